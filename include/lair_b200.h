@@ -1,0 +1,140 @@
+/*
+ * lair_b200.h -- C ABI of the B200-native LU path (getrf / getrs) behind lair's API.
+ *
+ * The reference (vinesystems/lair v0.8.0, pure Rust) has NO FFI for this path; the
+ * drop-in boundary is two generic Rust signatures and their callers:
+ *
+ *   lapack::getrf<A>(a: ArrayViewMut2<A>) -> (Vec<usize>, Option<usize>)   src/lapack/getrf.rs:12-27
+ *   lapack::getrs<A,SA,SB>(a, p: &[usize], b: &ArrayBase<SB,Ix1>) -> Array1<A>   src/lapack/getrs.rs:12-38
+ *   lapack::laswp<T>(ncols, a, row_stride, col_stride, begin, piv)          src/lapack/laswp.rs:11-40
+ *   lu::Factorized::from / ::solve / ::is_singular                          src/decomposition/lu.rs:156-171, 87-98, 75-77
+ *   equation::solve                                                          src/equation.rs:32-60
+ *
+ * Every entry point below is what a thin Rust shim (rust/src/ffi.rs)
+ * binds underneath those unchanged signatures.  Plain pointers and sizes only; no
+ * torch / C++ types.  All functions return a lair_b200_status (0 = ok); the message of
+ * the last failure on the calling thread is available from lair_b200_last_error().
+ * There is NO CPU fallback: without a usable sm_100 device every compute entry point
+ * returns LAIR_B200_ERR_NO_DEVICE (the Rust shim turns non-zero into panic!, because the
+ * reference signatures have no error channel for runtime failure).
+ *
+ * Conventions shared with the reference:
+ *   - strides are in ELEMENTS and may be negative or transposed (getrf.rs:52-54, tests :430-483);
+ *   - ipiv is the 0-based LAPACK-style sequential interchange vector of length min(m,n)
+ *     (getrf.rs:18-19): row i was swapped with row ipiv[i] at step i;
+ *   - *info = -1 for None, else the LAST step whose pivot was exactly zero
+ *     (getrf.rs:72-73, 168-169; differs from LAPACK's first-zero, 1-based info);
+ *   - pivot search = first index of max |re|+|im|, NaN never wins (src/blas/iamax.rs:6-21);
+ *   - complex scalars are interleaved (re, im) pairs, as num_complex::Complex<T> / C99.
+ */
+#ifndef LAIR_B200_H
+#define LAIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LAIR_B200_API __attribute__((visibility("default")))
+#else
+#define LAIR_B200_API
+#endif
+
+typedef enum lair_b200_status {
+    LAIR_B200_OK = 0,
+    LAIR_B200_ERR_INVALID = 1,     /* bad argument (shape / stride / null pointer)            */
+    LAIR_B200_ERR_NO_DEVICE = 2,   /* no CUDA device, or device is not sm_100                 */
+    LAIR_B200_ERR_CUDA = 3,        /* a CUDA runtime call or kernel failed                    */
+    LAIR_B200_ERR_ALLOC = 4,       /* host or device allocation failed                        */
+    LAIR_B200_ERR_UNSUPPORTED = 5, /* shape/type combination not implemented on the device    */
+    LAIR_B200_ERR_NCCL = 6         /* NCCL could not be loaded or a collective failed         */
+} lair_b200_status;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Library version: major*10000 + minor*100 + patch. */
+LAIR_B200_API int lair_b200_version(void);
+/* Message for the last non-zero status returned on this thread ("" if none). */
+LAIR_B200_API const char* lair_b200_last_error(void);
+/* Number of visible CUDA devices (0 and LAIR_B200_ERR_NO_DEVICE when none). */
+LAIR_B200_API int lair_b200_device_count(int* count);
+/* Bind the process-wide context to `device` (creates streams and workspaces lazily;
+ * idempotent for the same device).  Compute entry points call this with the current
+ * device if it was never called. */
+LAIR_B200_API int lair_b200_init(int device);
+LAIR_B200_API int lair_b200_shutdown(void);
+
+/* ---- host-pointer drop-ins (what the Rust shim binds) ---------------------------------
+ * getrf: factor the m x n host matrix `a` in place through its strides; H2D / D2H copies
+ * are inside the call.  Replaces src/lapack/getrf.rs:12-27 (and through it
+ * lu::Factorized::from, src/decomposition/lu.rs:163-170).
+ *   ipiv: min(m,n) int64 (widen to usize in the shim); info: see above.             */
+LAIR_B200_API int lair_b200_sgetrf(int64_t m, int64_t n, float* a, int64_t row_stride, int64_t col_stride, int64_t* ipiv, int64_t* info);
+LAIR_B200_API int lair_b200_dgetrf(int64_t m, int64_t n, double* a, int64_t row_stride, int64_t col_stride, int64_t* ipiv, int64_t* info);
+LAIR_B200_API int lair_b200_cgetrf(int64_t m, int64_t n, void* a, int64_t row_stride, int64_t col_stride, int64_t* ipiv, int64_t* info);
+LAIR_B200_API int lair_b200_zgetrf(int64_t m, int64_t n, void* a, int64_t row_stride, int64_t col_stride, int64_t* ipiv, int64_t* info);
+
+/* getrs: X = U^-1 L^-1 P B for nrhs right-hand sides.  Replaces src/lapack/getrs.rs:12-38
+ * (nrhs = 1, b_cs / x_cs ignored) and adds the multi-RHS form the reference lacks
+ * (SURVEY 0.5): column r of X equals the reference's getrs on column r of B.
+ * `lu` is n x n (any strides), ipiv has n entries, b / x are n x nrhs (any strides; x may
+ * alias b only if their strides are identical).                                       */
+LAIR_B200_API int lair_b200_sgetrs(int64_t n, int64_t nrhs, const float* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const float* b, int64_t b_rs, int64_t b_cs, float* x, int64_t x_rs, int64_t x_cs);
+LAIR_B200_API int lair_b200_dgetrs(int64_t n, int64_t nrhs, const double* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const double* b, int64_t b_rs, int64_t b_cs, double* x, int64_t x_rs, int64_t x_cs);
+LAIR_B200_API int lair_b200_cgetrs(int64_t n, int64_t nrhs, const void* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const void* b, int64_t b_rs, int64_t b_cs, void* x, int64_t x_rs, int64_t x_cs);
+LAIR_B200_API int lair_b200_zgetrs(int64_t n, int64_t nrhs, const void* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const void* b, int64_t b_rs, int64_t b_cs, void* x, int64_t x_rs, int64_t x_cs);
+
+/* gesv: the whole of equation::solve (src/equation.rs:32-60) in one call -- A is copied
+ * (never modified), factored on the device, and the factors stay device-resident for the
+ * solve (no D2H/H2D of L\U in between).  *info as getrf; when *info >= 0 the reference
+ * returns Err(InvalidInput::Value) and x is left untouched.                          */
+LAIR_B200_API int lair_b200_sgesv(int64_t n, int64_t nrhs, const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* x, int64_t x_rs, int64_t x_cs, int64_t* info);
+LAIR_B200_API int lair_b200_dgesv(int64_t n, int64_t nrhs, const double* a, int64_t a_rs, int64_t a_cs, const double* b, int64_t b_rs, int64_t b_cs, double* x, int64_t x_rs, int64_t x_cs, int64_t* info);
+
+/* Batched LU of `batch` independent, contiguous, row-major n x n matrices (n <= 32),
+ * i.e. `batch` calls of getrf.rs:12-27 on standard-layout inputs; results are bit-identical
+ * to the reference's row-major body (getrf.rs:46-120).  ipiv: batch*n int32, info: batch
+ * int32 (-1 = None).                                                                   */
+LAIR_B200_API int lair_b200_sgetrf_batched(int64_t batch, int64_t n, float* a, int32_t* ipiv, int32_t* info);
+LAIR_B200_API int lair_b200_dgetrf_batched(int64_t batch, int64_t n, double* a, int32_t* ipiv, int32_t* info);
+
+/* ---- device-resident variants (device pointers, caller's stream, no copies) -----------
+ * Used by the benchmark for the HBM-resident number and by callers that keep data on the
+ * GPU.  Device layout is ROW-MAJOR with leading dimension `lda` (elements, >= n).
+ * d_ipiv: int32[min(m,n)] global 0-based rows; d_info: int32[1].  `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  Asynchronous w.r.t. the host. */
+LAIR_B200_API int lair_b200_sgetrf_dev(int64_t m, int64_t n, float* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
+LAIR_B200_API int lair_b200_dgetrf_dev(int64_t m, int64_t n, double* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
+/* In-place solve on the device: d_b (n x nrhs, row-major, ldb) is overwritten with X. */
+LAIR_B200_API int lair_b200_sgetrs_dev(int64_t n, int64_t nrhs, const float* d_lu, int64_t lda, const int32_t* d_ipiv, float* d_b, int64_t ldb, void* stream);
+LAIR_B200_API int lair_b200_dgetrs_dev(int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, const int32_t* d_ipiv, double* d_b, int64_t ldb, void* stream);
+LAIR_B200_API int lair_b200_sgetrf_batched_dev(int64_t batch, int64_t n, float* d_a, int32_t* d_ipiv, int32_t* d_info, void* stream);
+LAIR_B200_API int lair_b200_dgetrf_batched_dev(int64_t batch, int64_t n, double* d_a, int32_t* d_ipiv, int32_t* d_info, void* stream);
+
+/* Building blocks of the blocked factorization, exported for parity tests and profiling
+ * (each mirrors one reference routine; all device-resident, row-major):
+ *   laswp  src/lapack/laswp.rs:11-40   rows of d_a[:, 0..ncols) swapped by d_ipiv[k0..k1)
+ *          (entries are global row indices relative to d_a's row 0)
+ *   trsm   src/blas/trsm.rs:6-22       B <- L^-1 B, L = unit-lower k x k at d_l
+ *   gemm   src/blas/gemm.rs:6-32       C -= A * B  (alpha = -1, no conjugation: the LU call site
+ *                                       src/lapack/getrf.rs:289-296)                     */
+LAIR_B200_API int lair_b200_dlaswp_dev(int64_t ncols, double* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, void* stream);
+LAIR_B200_API int lair_b200_slaswp_dev(int64_t ncols, float* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, void* stream);
+LAIR_B200_API int lair_b200_dtrsm_dev(int64_t k, int64_t ncols, const double* d_l, int64_t ldl, double* d_b, int64_t ldb, void* stream);
+LAIR_B200_API int lair_b200_strsm_dev(int64_t k, int64_t ncols, const float* d_l, int64_t ldl, float* d_b, int64_t ldb, void* stream);
+LAIR_B200_API int lair_b200_dgemm_minus_dev(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, const double* d_b, int64_t ldb, double* d_c, int64_t ldc, void* stream);
+LAIR_B200_API int lair_b200_sgemm_minus_dev(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc, void* stream);
+
+/* Tuning knobs (also read from the environment at init: LAIR_B200_NB, LAIR_B200_SMALL_N).
+ * name in {"nb", "small_n", "lookahead"}; returns LAIR_B200_ERR_INVALID for unknown names. */
+LAIR_B200_API int lair_b200_set_option(const char* name, int64_t value);
+LAIR_B200_API int lair_b200_get_option(const char* name, int64_t* value);
+/* Number of kernels this library has launched since init (for gpu_launches accounting). */
+LAIR_B200_API int64_t lair_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAIR_B200_H */

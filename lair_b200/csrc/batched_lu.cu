@@ -1,0 +1,208 @@
+// Batched LU of independent n x n (n <= 32) row-major matrices: one warp per matrix,
+// one matrix row per lane, the whole matrix on chip.  HBM-bound path:
+// algorithmic traffic = 2*n*n*sizeof(T) + 4*n bytes per matrix.
+//
+// Arithmetic follows the reference's row-major body step for step
+// (src/lapack/getrf.rs:46-120): first-max pivot (src/blas/iamax.rs:6-21), reciprocal
+// multiply for the multipliers, then a rounded multiply and a rounded subtract per
+// element -- so L\U, ipiv and info are BIT-IDENTICAL to the reference.
+//
+// Row interchanges are logical: a lane keeps its row in registers for the whole
+// factorization and only its position `pos` changes; rows are written to their final
+// positions through shared memory at the end (coalesced 128-bit global stores).
+#include "common.cuh"
+#include "pivot_key.cuh"
+
+namespace lair {
+namespace {
+
+constexpr unsigned kFull = kFullMask;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <class T> struct Vec16;  // 16-byte vector of T
+template <> struct Vec16<float> { using type = float4; static constexpr int n = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int n = 2; };
+
+template <class T, int WARPS, int MINB, bool FULL>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __restrict__ info, long long batch, int n) {
+    constexpr int N = 32;
+    using V = typename Vec16<T>::type;
+    constexpr int VEC = Vec16<T>::n;
+    constexpr int LD = N + VEC;           // padded smem row: conflict-free 128-bit row reads
+    constexpr int CPR = N / VEC;          // 16-byte chunks per row
+    using K = PivotKey<T>;
+    using O = Ops<T>;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* mat = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (N * LD + 2 * LD);
+    T* rowbuf = mat + N * LD;
+
+    const long long warp_global = (long long)blockIdx.x * WARPS + warp;
+    const long long warp_total = (long long)gridDim.x * WARPS;
+
+    for (long long mi = warp_global; mi < batch; mi += warp_total) {
+        T* g = A + mi * (long long)n * n;
+        // ---- stage the matrix: coalesced global -> padded shared ----
+        if (FULL) {
+#pragma unroll
+            for (int c = lane; c < N * CPR; c += 32) {
+                int r = c / CPR, cc = c % CPR;
+                cp_async16(mat + r * LD + cc * VEC, g + (size_t)c * VEC);
+            }
+            cp_async_wait_all();
+        } else {
+            // n < 32: embed in diag(A, I) so the extra steps are no-ops
+            for (int idx = lane; idx < N * N; idx += 32) {
+                int r = idx >> 5, c = idx & 31;
+                T v = (r == c) ? O::one() : O::zero();
+                if (r < n && c < n) v = g[r * n + c];
+                mat[r * LD + c] = v;
+            }
+        }
+        __syncwarp();
+        T a[N];
+#pragma unroll
+        for (int c = 0; c < CPR; ++c) {
+            V v = *reinterpret_cast<const V*>(mat + lane * LD + c * VEC);
+            const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) a[c * VEC + e] = pv[e];
+        }
+        __syncwarp();
+
+        int pos = lane;      // current logical row of the row this lane owns
+        int mypiv = lane;    // lane j records ipiv[j]; identity unless a swap happens (getrf.rs:18-19,62-64)
+        int sing = -1;
+
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (!FULL && j >= n) break;
+            // -- iamax over logical rows >= j (iamax.rs:10-19) --
+            const bool live = pos >= j;
+            typename K::type key = live ? K::of(a[j]) : (typename K::type)0;
+            typename K::type kmax = K::warp_max(key);
+            if (kmax == 0) {  // max_val == 0: singular step, no swap, no update (getrf.rs:72-73)
+                sing = j;
+                continue;
+            }
+            const bool cand = live && (key == kmax);
+            // strict `>` in the reference == lowest logical row among equal maxima
+            const unsigned ppos = __reduce_min_sync(kFull, cand ? (unsigned)pos : 0xffffffffu);
+            const bool is_w = cand && ((unsigned)pos == ppos);
+            if (lane == j) mypiv = (int)ppos;
+            if (pos == j) pos = (int)ppos;  // the row sitting at j moves to the pivot's old place
+            if (is_w) pos = j;              // the pivot row moves to j
+            // -- broadcast the pivot row (columns >= j) through shared memory --
+            const int c0 = j / VEC;
+            T* rb = rowbuf + (j & 1) * LD;
+            if (is_w) {
+#pragma unroll
+                for (int c = c0; c < CPR; ++c) {
+                    V v;
+                    T* pv = reinterpret_cast<T*>(&v);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) pv[e] = a[c * VEC + e];
+                    *reinterpret_cast<V*>(rb + c * VEC) = v;
+                }
+            }
+            __syncwarp();
+            T u[N];
+#pragma unroll
+            for (int c = c0; c < CPR; ++c) {
+                V v = *reinterpret_cast<const V*>(rb + c * VEC);
+                const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) u[c * VEC + e] = pv[e];
+            }
+            const T recip = O::recip(u[j]);  // A::one() / pivot (getrf.rs:76)
+            if (pos > j) {
+                const T l = O::mul(a[j], recip);  // *row_j *= pivot_recip (getrf.rs:81)
+                a[j] = l;
+#pragma unroll
+                for (int k = j + 1; k < N; ++k) a[k] = O::sub(a[k], O::mul(l, u[k]));  // getrf.rs:86-87
+            }
+        }
+
+        // ---- rows to their final positions, then coalesced store ----
+#pragma unroll
+        for (int c = 0; c < CPR; ++c) {
+            V v;
+            T* pv = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) pv[e] = a[c * VEC + e];
+            *reinterpret_cast<V*>(mat + pos * LD + c * VEC) = v;
+        }
+        __syncwarp();
+        if (FULL) {
+#pragma unroll
+            for (int c = lane; c < N * CPR; c += 32) {
+                int r = c / CPR, cc = c % CPR;
+                *reinterpret_cast<V*>(g + (size_t)c * VEC) = *reinterpret_cast<const V*>(mat + r * LD + cc * VEC);
+            }
+            ipiv[mi * N + lane] = mypiv;
+        } else {
+            for (int idx = lane; idx < n * n; idx += 32) {
+                int r = idx / n, c = idx % n;
+                g[idx] = mat[r * LD + c];
+            }
+            if (lane < n) ipiv[mi * n + lane] = mypiv;
+        }
+        if (lane == 0) info[mi] = sing;
+        __syncwarp();
+    }
+}
+
+template <class T, int WARPS, int MINB, bool FULL>
+int launch_batched(long long batch, int n, T* d_a, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s) {
+    constexpr int N = 32, VEC = Vec16<T>::n, LD = N + VEC;
+    auto kern = batched_lu32_kernel<T, WARPS, MINB, FULL>;
+    size_t smem = (size_t)WARPS * (N * LD + 2 * LD) * sizeof(T);
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAIR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    long long want = (batch + WARPS - 1) / WARPS;
+    long long cap = (long long)ctx().sm_count * blocks_per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) return LAIR_B200_OK;
+    kern<<<grid, WARPS * 32, smem, s>>>(d_a, d_ipiv, d_info, batch, n);
+    LAIR_LAUNCH_CHECK();
+    return LAIR_B200_OK;
+}
+
+}  // namespace
+
+template <class T>
+int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s) {
+    LAIR_REQUIRE(batch >= 0 && n >= 0, "batched getrf: negative size");
+    LAIR_REQUIRE(n <= 32, "batched getrf supports n <= 32 (got %lld)", (long long)n);
+    if (batch == 0 || n == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(d_a && d_ipiv && d_info, "batched getrf: null pointer");
+    const bool full = (n == 32) && (reinterpret_cast<uintptr_t>(d_a) % 16 == 0);
+    // Occupancy variants: fewer registers (small spills) vs fewer resident warps; the
+    // default was picked on a B200 (profiles/), LAIR_B200_BATCHED_CFG=1 selects the other.
+    constexpr int kLo = sizeof(T) == 8 ? 3 : 5;  // no spills
+    constexpr int kHi = sizeof(T) == 8 ? 4 : 8;  // max occupancy
+    const int64_t cfg = ctx().opt.batched_cfg;
+    if (full) {
+        if (cfg == 1) return launch_batched<T, 4, kHi, true>(batch, 32, d_a, d_ipiv, d_info, s);
+        return launch_batched<T, 4, kLo, true>(batch, 32, d_a, d_ipiv, d_info, s);
+    }
+    return launch_batched<T, 4, kLo, false>(batch, (int)n, d_a, d_ipiv, d_info, s);
+}
+
+template int getrf_batched_dev<float>(int64_t, int64_t, float*, int32_t*, int32_t*, cudaStream_t);
+template int getrf_batched_dev<double>(int64_t, int64_t, double*, int32_t*, int32_t*, cudaStream_t);
+
+}  // namespace lair

@@ -1,0 +1,290 @@
+// extern "C" entry points declared in include/lair_b200.h: argument checks, dispatch between
+// the single-CTA exact kernel and the blocked factorization, host <-> device marshalling.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "host_io.cuh"
+
+namespace lair {
+
+static std::mutex g_call_mu;  // host-pointer entry points serialise on the library stream
+
+// ---- dispatch ------------------------------------------------------------------------------
+template <class T> struct IsReal { static constexpr bool value = !Ops<T>::is_complex; };
+
+template <class T>
+static bool fits_small(int64_t m, int64_t n) {
+    const int64_t lim = ctx().opt.small_n;
+    return (m <= lim && n <= lim);
+}
+
+template <class T>
+int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout,
+              cudaStream_t s) {
+    if (fits_small<T>(m, n)) return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
+    if constexpr (IsReal<T>::value) {
+        return getrf_blocked_dev<T>(m, n, d_a, lda, d_ipiv, d_info, s);
+    } else {
+        // complex beyond the single-CTA limit: correct-first in-place path
+        return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
+    }
+}
+
+template <class T>
+int getrs_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb,
+              cudaStream_t s) {
+    if (n <= ctx().opt.small_n || !IsReal<T>::value) return getrs_small_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+    if constexpr (IsReal<T>::value) return getrs_blocked_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+    return LAIR_B200_ERR_UNSUPPORTED;
+}
+
+static int64_t device_ld(int64_t n) {
+    // keep rows 128-byte friendly for the blocked kernels; small matrices stay dense
+    if (n <= ctx().opt.small_n) return n;
+    return (n + 31) / 32 * 32;
+}
+
+// ---- host-pointer getrf --------------------------------------------------------------------
+template <class T>
+static int getrf_host(int64_t m, int64_t n, T* a, int64_t rs, int64_t cs, int64_t* ipiv, int64_t* info) {
+    LAIR_REQUIRE(m >= 0 && n >= 0, "getrf: negative dimension (m=%lld, n=%lld)", (long long)m, (long long)n);
+    LAIR_REQUIRE(info != nullptr, "getrf: info is null");
+    const int64_t k = m < n ? m : n;
+    *info = -1;
+    if (k == 0) return LAIR_B200_OK;  // getrf.rs:350-355: empty -> ([], None)
+    LAIR_REQUIRE(a != nullptr && ipiv != nullptr, "getrf: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    const bool std_layout = is_standard_layout(m, n, rs, cs);
+    const int64_t ld = device_ld(n);
+    void *dA = nullptr, *dP = nullptr, *dI = nullptr;
+    LAIR_CHECK(pool().get(DevicePool::kMatrix, (size_t)m * ld * sizeof(T), &dA));
+    LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)k * sizeof(int32_t), &dP));
+    LAIR_CHECK(pool().get(DevicePool::kInfo, sizeof(int32_t), &dI));
+    LAIR_CHECK(upload_matrix<T>(a, m, n, rs, cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CHECK(getrf_dev<T>(m, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s));
+    LAIR_CHECK(download_matrix<T>(a, m, n, rs, cs, (const T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CHECK(download_ipiv64(ipiv, (const int32_t*)dP, k, DevicePool::kPivots64, s));
+    int32_t info32 = -1;
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(&info32, dI, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    *info = info32;
+    return LAIR_B200_OK;
+}
+
+// ---- host-pointer getrs / gesv --------------------------------------------------------------
+template <class T>
+static int upload_ipiv32(const int64_t* ipiv, int64_t n, int32_t* d, cudaStream_t s) {
+    std::vector<int32_t> p((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        LAIR_REQUIRE(ipiv[i] >= 0 && ipiv[i] < n, "getrs: ipiv[%lld]=%lld out of range", (long long)i, (long long)ipiv[i]);
+        p[(size_t)i] = (int32_t)ipiv[i];
+    }
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(d, p.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return LAIR_B200_OK;
+}
+
+template <class T>
+static int getrs_host(int64_t n, int64_t nrhs, const T* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const T* b,
+                      int64_t b_rs, int64_t b_cs, T* x, int64_t x_rs, int64_t x_cs) {
+    LAIR_REQUIRE(n >= 0 && nrhs >= 0, "getrs: negative dimension");
+    if (n == 0 || nrhs == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(lu && ipiv && b && x, "getrs: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    const int64_t ld = device_ld(n);
+    const int64_t ldb = nrhs;
+    void *dA = nullptr, *dB = nullptr, *dP = nullptr;
+    LAIR_CHECK(pool().get(DevicePool::kMatrix, (size_t)n * ld * sizeof(T), &dA));
+    LAIR_CHECK(pool().get(DevicePool::kRhs, (size_t)n * ldb * sizeof(T), &dB));
+    LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)n * sizeof(int32_t), &dP));
+    LAIR_CHECK(upload_matrix<T>(lu, n, n, lu_rs, lu_cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CHECK(upload_matrix<T>(b, n, nrhs, b_rs, b_cs, (T*)dB, ldb, DevicePool::kTmpB, s));
+    LAIR_CHECK(upload_ipiv32<T>(ipiv, n, (int32_t*)dP, s));
+    LAIR_CHECK(getrs_dev<T>(n, nrhs, (const T*)dA, ld, (const int32_t*)dP, (T*)dB, ldb, s));
+    LAIR_CHECK(download_matrix<T>(x, n, nrhs, x_rs, x_cs, (const T*)dB, ldb, DevicePool::kTmpB, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return LAIR_B200_OK;
+}
+
+template <class T>
+static int gesv_host(int64_t n, int64_t nrhs, const T* a, int64_t a_rs, int64_t a_cs, const T* b, int64_t b_rs,
+                     int64_t b_cs, T* x, int64_t x_rs, int64_t x_cs, int64_t* info) {
+    LAIR_REQUIRE(n >= 0 && nrhs >= 0, "gesv: negative dimension");
+    LAIR_REQUIRE(info != nullptr, "gesv: info is null");
+    *info = -1;
+    if (n == 0 || nrhs == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(a && b && x, "gesv: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    const bool std_layout = is_standard_layout(n, n, a_rs, a_cs);
+    const int64_t ld = device_ld(n);
+    const int64_t ldb = nrhs;
+    void *dA = nullptr, *dB = nullptr, *dP = nullptr, *dI = nullptr;
+    LAIR_CHECK(pool().get(DevicePool::kMatrix, (size_t)n * ld * sizeof(T), &dA));
+    LAIR_CHECK(pool().get(DevicePool::kRhs, (size_t)n * ldb * sizeof(T), &dB));
+    LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)n * sizeof(int32_t), &dP));
+    LAIR_CHECK(pool().get(DevicePool::kInfo, sizeof(int32_t), &dI));
+    LAIR_CHECK(upload_matrix<T>(a, n, n, a_rs, a_cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CHECK(upload_matrix<T>(b, n, nrhs, b_rs, b_cs, (T*)dB, ldb, DevicePool::kTmpB, s));
+    LAIR_CHECK(getrf_dev<T>(n, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s));
+    int32_t info32 = -1;
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(&info32, dI, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    *info = info32;
+    if (info32 >= 0) return LAIR_B200_OK;  // singular: equation.rs:55-56 returns Err(Value), no solve
+    LAIR_CHECK(getrs_dev<T>(n, nrhs, (const T*)dA, ld, (const int32_t*)dP, (T*)dB, ldb, s));
+    LAIR_CHECK(download_matrix<T>(x, n, nrhs, x_rs, x_cs, (const T*)dB, ldb, DevicePool::kTmpB, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return LAIR_B200_OK;
+}
+
+template <class T>
+static int getrf_batched_host(int64_t batch, int64_t n, T* a, int32_t* ipiv, int32_t* info) {
+    LAIR_REQUIRE(batch >= 0 && n >= 0 && n <= 32, "getrf_batched: need batch >= 0 and 0 <= n <= 32");
+    if (batch == 0 || n == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(a && ipiv && info, "getrf_batched: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    void *dA = nullptr, *dP = nullptr, *dI = nullptr;
+    size_t abytes = (size_t)batch * n * n * sizeof(T);
+    LAIR_CHECK(pool().get(DevicePool::kMatrix, abytes, &dA));
+    LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)batch * n * sizeof(int32_t), &dP));
+    LAIR_CHECK(pool().get(DevicePool::kMisc, (size_t)batch * sizeof(int32_t), &dI));
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(dA, a, abytes, cudaMemcpyHostToDevice, s));
+    LAIR_CHECK(getrf_batched_dev<T>(batch, n, (T*)dA, (int32_t*)dP, (int32_t*)dI, s));
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(a, dA, abytes, cudaMemcpyDeviceToHost, s));
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(ipiv, dP, (size_t)batch * n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(info, dI, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return LAIR_B200_OK;
+}
+
+#define INST_DISPATCH(T)                                                                                         \
+    template int getrf_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t);           \
+    template int getrs_dev<T>(int64_t, int64_t, const T*, int64_t, const int32_t*, T*, int64_t, cudaStream_t);
+INST_DISPATCH(float)
+INST_DISPATCH(double)
+INST_DISPATCH(cxf)
+INST_DISPATCH(cxd)
+
+}  // namespace lair
+
+using namespace lair;
+
+#define DEV_PROLOGUE()        \
+    LAIR_CHECK(ensure_init()); \
+    cudaStream_t s = (cudaStream_t)stream
+
+extern "C" {
+
+int lair_b200_sgetrf(int64_t m, int64_t n, float* a, int64_t rs, int64_t cs, int64_t* ipiv, int64_t* info) {
+    return getrf_host<float>(m, n, a, rs, cs, ipiv, info);
+}
+int lair_b200_dgetrf(int64_t m, int64_t n, double* a, int64_t rs, int64_t cs, int64_t* ipiv, int64_t* info) {
+    return getrf_host<double>(m, n, a, rs, cs, ipiv, info);
+}
+int lair_b200_cgetrf(int64_t m, int64_t n, void* a, int64_t rs, int64_t cs, int64_t* ipiv, int64_t* info) {
+    return getrf_host<cxf>(m, n, (cxf*)a, rs, cs, ipiv, info);
+}
+int lair_b200_zgetrf(int64_t m, int64_t n, void* a, int64_t rs, int64_t cs, int64_t* ipiv, int64_t* info) {
+    return getrf_host<cxd>(m, n, (cxd*)a, rs, cs, ipiv, info);
+}
+
+int lair_b200_sgetrs(int64_t n, int64_t nrhs, const float* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv,
+                     const float* b, int64_t b_rs, int64_t b_cs, float* x, int64_t x_rs, int64_t x_cs) {
+    return getrs_host<float>(n, nrhs, lu, lu_rs, lu_cs, ipiv, b, b_rs, b_cs, x, x_rs, x_cs);
+}
+int lair_b200_dgetrs(int64_t n, int64_t nrhs, const double* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv,
+                     const double* b, int64_t b_rs, int64_t b_cs, double* x, int64_t x_rs, int64_t x_cs) {
+    return getrs_host<double>(n, nrhs, lu, lu_rs, lu_cs, ipiv, b, b_rs, b_cs, x, x_rs, x_cs);
+}
+int lair_b200_cgetrs(int64_t n, int64_t nrhs, const void* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv,
+                     const void* b, int64_t b_rs, int64_t b_cs, void* x, int64_t x_rs, int64_t x_cs) {
+    return getrs_host<cxf>(n, nrhs, (const cxf*)lu, lu_rs, lu_cs, ipiv, (const cxf*)b, b_rs, b_cs, (cxf*)x, x_rs, x_cs);
+}
+int lair_b200_zgetrs(int64_t n, int64_t nrhs, const void* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv,
+                     const void* b, int64_t b_rs, int64_t b_cs, void* x, int64_t x_rs, int64_t x_cs) {
+    return getrs_host<cxd>(n, nrhs, (const cxd*)lu, lu_rs, lu_cs, ipiv, (const cxd*)b, b_rs, b_cs, (cxd*)x, x_rs, x_cs);
+}
+
+int lair_b200_sgesv(int64_t n, int64_t nrhs, const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs,
+                    int64_t b_cs, float* x, int64_t x_rs, int64_t x_cs, int64_t* info) {
+    return gesv_host<float>(n, nrhs, a, a_rs, a_cs, b, b_rs, b_cs, x, x_rs, x_cs, info);
+}
+int lair_b200_dgesv(int64_t n, int64_t nrhs, const double* a, int64_t a_rs, int64_t a_cs, const double* b, int64_t b_rs,
+                    int64_t b_cs, double* x, int64_t x_rs, int64_t x_cs, int64_t* info) {
+    return gesv_host<double>(n, nrhs, a, a_rs, a_cs, b, b_rs, b_cs, x, x_rs, x_cs, info);
+}
+
+int lair_b200_sgetrf_batched(int64_t batch, int64_t n, float* a, int32_t* ipiv, int32_t* info) {
+    return getrf_batched_host<float>(batch, n, a, ipiv, info);
+}
+int lair_b200_dgetrf_batched(int64_t batch, int64_t n, double* a, int32_t* ipiv, int32_t* info) {
+    return getrf_batched_host<double>(batch, n, a, ipiv, info);
+}
+
+// ---- device-resident -------------------------------------------------------------------------
+int lair_b200_sgetrf_dev(int64_t m, int64_t n, float* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream) {
+    DEV_PROLOGUE();
+    LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf_dev: bad shape");
+    return getrf_dev<float>(m, n, d_a, lda, d_ipiv, d_info, true, s);
+}
+int lair_b200_dgetrf_dev(int64_t m, int64_t n, double* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream) {
+    DEV_PROLOGUE();
+    LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf_dev: bad shape");
+    return getrf_dev<double>(m, n, d_a, lda, d_ipiv, d_info, true, s);
+}
+int lair_b200_sgetrs_dev(int64_t n, int64_t nrhs, const float* d_lu, int64_t lda, const int32_t* d_ipiv, float* d_b,
+                         int64_t ldb, void* stream) {
+    DEV_PROLOGUE();
+    return getrs_dev<float>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+}
+int lair_b200_dgetrs_dev(int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, const int32_t* d_ipiv, double* d_b,
+                         int64_t ldb, void* stream) {
+    DEV_PROLOGUE();
+    return getrs_dev<double>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+}
+int lair_b200_sgetrf_batched_dev(int64_t batch, int64_t n, float* d_a, int32_t* d_ipiv, int32_t* d_info, void* stream) {
+    DEV_PROLOGUE();
+    return getrf_batched_dev<float>(batch, n, d_a, d_ipiv, d_info, s);
+}
+int lair_b200_dgetrf_batched_dev(int64_t batch, int64_t n, double* d_a, int32_t* d_ipiv, int32_t* d_info, void* stream) {
+    DEV_PROLOGUE();
+    return getrf_batched_dev<double>(batch, n, d_a, d_ipiv, d_info, s);
+}
+
+int lair_b200_dlaswp_dev(int64_t ncols, double* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, void* stream) {
+    DEV_PROLOGUE();
+    return laswp_dev<double>(ncols, d_a, lda, k0, k1, d_ipiv, s);
+}
+int lair_b200_slaswp_dev(int64_t ncols, float* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, void* stream) {
+    DEV_PROLOGUE();
+    return laswp_dev<float>(ncols, d_a, lda, k0, k1, d_ipiv, s);
+}
+int lair_b200_dtrsm_dev(int64_t k, int64_t ncols, const double* d_l, int64_t ldl, double* d_b, int64_t ldb, void* stream) {
+    DEV_PROLOGUE();
+    return trsm_lower_unit_dev<double>(k, ncols, d_l, ldl, d_b, ldb, s);
+}
+int lair_b200_strsm_dev(int64_t k, int64_t ncols, const float* d_l, int64_t ldl, float* d_b, int64_t ldb, void* stream) {
+    DEV_PROLOGUE();
+    return trsm_lower_unit_dev<float>(k, ncols, d_l, ldl, d_b, ldb, s);
+}
+int lair_b200_dgemm_minus_dev(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, const double* d_b,
+                              int64_t ldb, double* d_c, int64_t ldc, void* stream) {
+    DEV_PROLOGUE();
+    return gemm_minus_dev<double>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);
+}
+int lair_b200_sgemm_minus_dev(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t lda, const float* d_b,
+                              int64_t ldb, float* d_c, int64_t ldc, void* stream) {
+    DEV_PROLOGUE();
+    return gemm_minus_dev<float>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);
+}
+
+}  // extern "C"

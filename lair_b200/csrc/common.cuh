@@ -1,0 +1,164 @@
+// Shared declarations for the lair_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/lair_b200.h"
+
+namespace lair {
+
+// ---- error plumbing ---------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local int g_last_status;
+
+#define LAIR_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::lair::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? LAIR_B200_ERR_ALLOC : LAIR_B200_ERR_CUDA; \
+        }                                                                                      \
+    } while (0)
+
+#define LAIR_CHECK(expr)                 \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != LAIR_B200_OK) return _s; \
+    } while (0)
+
+#define LAIR_REQUIRE(cond, ...)              \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::lair::set_error(__VA_ARGS__);  \
+            return LAIR_B200_ERR_INVALID;    \
+        }                                    \
+    } while (0)
+
+// Counts kernels launched by this library (lair_b200_launch_count).
+void count_launch(int n = 1);
+#define LAIR_LAUNCH_CHECK()                      \
+    do {                                         \
+        ::lair::count_launch();                  \
+        LAIR_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
+
+// ---- scalar layer: exact (never FMA-contracted) arithmetic ------------------------------
+// The reference is Rust: `a -= l * u` is a rounded multiply followed by a rounded
+// subtract (src/lapack/getrf.rs:86-87).  The *_rn intrinsics are never contracted by
+// nvcc, so kernels that promise bit-identical results use these.
+template <class T>
+struct cx {
+    T re, im;
+};
+using cxf = cx<float>;
+using cxd = cx<double>;
+
+template <class T> struct Ops;
+
+template <> struct Ops<float> {
+    using Real = float;
+    static constexpr bool is_complex = false;
+    __host__ __device__ static float zero() { return 0.f; }
+    __host__ __device__ static float one() { return 1.f; }
+    __device__ static float mul(float a, float b) { return __fmul_rn(a, b); }
+    __device__ static float add(float a, float b) { return __fadd_rn(a, b); }
+    __device__ static float sub(float a, float b) { return __fsub_rn(a, b); }
+    __device__ static float div(float a, float b) { return __fdiv_rn(a, b); }
+    __device__ static float recip(float a) { return __fdiv_rn(1.f, a); }
+    __device__ static float abs1(float a) { return fabsf(a); }
+    __device__ static bool is_zero(float a) { return a == 0.f; }
+};
+template <> struct Ops<double> {
+    using Real = double;
+    static constexpr bool is_complex = false;
+    __host__ __device__ static double zero() { return 0.0; }
+    __host__ __device__ static double one() { return 1.0; }
+    __device__ static double mul(double a, double b) { return __dmul_rn(a, b); }
+    __device__ static double add(double a, double b) { return __dadd_rn(a, b); }
+    __device__ static double sub(double a, double b) { return __dsub_rn(a, b); }
+    __device__ static double div(double a, double b) { return __ddiv_rn(a, b); }
+    __device__ static double recip(double a) { return __ddiv_rn(1.0, a); }
+    __device__ static double abs1(double a) { return fabs(a); }
+    __device__ static bool is_zero(double a) { return a == 0.0; }
+};
+// Complex follows num-complex 0.4's textbook formulas (the reference's dependency,
+// Cargo.toml:24), exactly like oracle/lair_oracle.hpp.
+template <class R> struct Ops<cx<R>> {
+    using Real = R;
+    using O = Ops<R>;
+    static constexpr bool is_complex = true;
+    __host__ __device__ static cx<R> zero() { return {R(0), R(0)}; }
+    __host__ __device__ static cx<R> one() { return {R(1), R(0)}; }
+    __device__ static cx<R> mul(cx<R> a, cx<R> b) {
+        return {O::sub(O::mul(a.re, b.re), O::mul(a.im, b.im)), O::add(O::mul(a.re, b.im), O::mul(a.im, b.re))};
+    }
+    __device__ static cx<R> add(cx<R> a, cx<R> b) { return {O::add(a.re, b.re), O::add(a.im, b.im)}; }
+    __device__ static cx<R> sub(cx<R> a, cx<R> b) { return {O::sub(a.re, b.re), O::sub(a.im, b.im)}; }
+    __device__ static cx<R> div(cx<R> a, cx<R> b) {
+        R ns = O::add(O::mul(b.re, b.re), O::mul(b.im, b.im));
+        R re = O::add(O::mul(a.re, b.re), O::mul(a.im, b.im));
+        R im = O::sub(O::mul(a.im, b.re), O::mul(a.re, b.im));
+        return {O::div(re, ns), O::div(im, ns)};
+    }
+    __device__ static cx<R> recip(cx<R> a) { return div(one(), a); }
+    __device__ static R abs1(cx<R> a) { return O::add(O::abs1(a.re), O::abs1(a.im)); }
+    __device__ static bool is_zero(cx<R> a) { return a.re == R(0) && a.im == R(0); }
+};
+
+// ---- process-wide context ----------------------------------------------------------------
+struct Options {
+    int64_t nb = 256;        // outer block width of the blocked factorization
+    int64_t small_n = 128;   // max(m, n) handled by the single-CTA exact kernel
+    int64_t lookahead = 1;   // overlap panel k+1 with trailing update k
+    int64_t batched_cfg = 0; // occupancy variant of the batched kernel (batched_lu.cu)
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;        // library-owned stream for the host-pointer entry points
+    cudaStream_t aux_stream = nullptr;    // second stream (lookahead / copy overlap)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // panel exchange workspace (see panel.cu)
+    void* panel_ws = nullptr;
+    size_t panel_ws_bytes = 0;
+    uint32_t panel_seq = 0;
+    // generic device scratch grown on demand
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    Options opt;
+};
+
+Context& ctx();
+int ensure_init();                                  // binds to the current device if needed
+int ensure_scratch(size_t bytes, void** out);       // device scratch >= bytes (may reallocate)
+
+// ---- kernels / device-resident routines (row-major, leading dimension in elements) --------
+template <class T> int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
+template <class T> int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s);
+template <class T> int getrs_small_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
+template <class T> int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
+template <class T> int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
+template <class T> int laswp_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s);
+template <class T> int trsm_lower_unit_dev(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* d_b, int64_t ldb, cudaStream_t s);
+template <class T> int trsm_upper_dev(int64_t k, int64_t ncols, const T* d_u, int64_t ldu, T* d_b, int64_t ldb, cudaStream_t s);
+template <class T> int gemm_minus_dev(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, const T* d_b, int64_t ldb, T* d_c, int64_t ldc, cudaStream_t s);
+// factor the (rows x w) panel at d_a (w <= panel width limit) with partial pivoting;
+// d_ipiv[0..w) receive row indices relative to d_a's row 0 plus `row_base`.
+template <class T> int panel_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
+template <class T> int panel_max_width(int64_t rows);
+// 1 if a panel exchange timed out since the last clear (results are then invalid)
+int panel_error_flag(bool clear);
+
+// ---- dispatch helpers ----------------------------------------------------------------------
+template <class T> int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s);
+template <class T> int getrs_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
+
+}  // namespace lair

@@ -1,0 +1,193 @@
+// Process-wide context: device binding, streams, workspaces, options, error string.
+#include <atomic>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace lair {
+
+thread_local int g_last_status = 0;
+static thread_local char g_err[1024] = {0};
+static std::atomic<int64_t> g_launches{0};
+static Context g_ctx;
+static std::mutex g_ctx_mu;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+Context& ctx() { return g_ctx; }
+
+static int init_locked(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); lair_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return LAIR_B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (0..%d)", device, count - 1);
+        return LAIR_B200_ERR_INVALID;
+    }
+    if (g_ctx.ready && g_ctx.device == device) {
+        LAIR_CUDA_CHECK(cudaSetDevice(device));
+        return LAIR_B200_OK;
+    }
+    if (g_ctx.ready) {
+        set_error("context already bound to device %d; call lair_b200_shutdown() first", g_ctx.device);
+        return LAIR_B200_ERR_INVALID;
+    }
+    LAIR_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LAIR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                  prop.minor);
+        return LAIR_B200_ERR_NO_DEVICE;
+    }
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.cc_major = prop.major;
+    g_ctx.cc_minor = prop.minor;
+    g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+    int lo = 0, hi = 0;
+    LAIR_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LAIR_CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.stream, cudaStreamNonBlocking, lo));
+    // the lookahead panel runs on the high-priority stream so its CTAs are placed first
+    LAIR_CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.aux_stream, cudaStreamNonBlocking, hi));
+    for (auto& ev : g_ctx.ev) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char* v = getenv("LAIR_B200_NB")) g_ctx.opt.nb = atoll(v);
+    if (const char* v = getenv("LAIR_B200_SMALL_N")) g_ctx.opt.small_n = atoll(v);
+    if (const char* v = getenv("LAIR_B200_LOOKAHEAD")) g_ctx.opt.lookahead = atoll(v);
+    if (const char* v = getenv("LAIR_B200_BATCHED_CFG")) g_ctx.opt.batched_cfg = atoll(v);
+    g_ctx.ready = true;
+    return LAIR_B200_OK;
+}
+
+int ensure_init() {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx.ready) {
+        LAIR_CUDA_CHECK(cudaSetDevice(g_ctx.device));
+        return LAIR_B200_OK;
+    }
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        dev = 0;
+    }
+    return init_locked(dev);
+}
+
+int ensure_scratch(size_t bytes, void** out) {
+    Context& c = g_ctx;
+    if (c.scratch_bytes < bytes) {
+        if (c.scratch) {
+            LAIR_CUDA_CHECK(cudaDeviceSynchronize());
+            LAIR_CUDA_CHECK(cudaFree(c.scratch));
+            c.scratch = nullptr;
+            c.scratch_bytes = 0;
+        }
+        size_t want = bytes + (bytes >> 2);
+        LAIR_CUDA_CHECK(cudaMalloc(&c.scratch, want));
+        c.scratch_bytes = want;
+    }
+    *out = c.scratch;
+    return LAIR_B200_OK;
+}
+
+}  // namespace lair
+
+using namespace lair;
+
+extern "C" {
+
+int lair_b200_version(void) { return 100; }  // 0.1.0
+
+const char* lair_b200_last_error(void) { return g_err; }
+
+int lair_b200_device_count(int* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        c = 0;
+    }
+    if (count) *count = c;
+    if (c == 0) {
+        set_error("no CUDA device available; lair_b200 has no CPU fallback");
+        return LAIR_B200_ERR_NO_DEVICE;
+    }
+    return LAIR_B200_OK;
+}
+
+int lair_b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    return init_locked(device);
+}
+
+int lair_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    Context& c = g_ctx;
+    if (!c.ready) return LAIR_B200_OK;
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    if (c.panel_ws) cudaFree(c.panel_ws);
+    if (c.scratch) cudaFree(c.scratch);
+    for (auto& ev : c.ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
+    c = Context();
+    return LAIR_B200_OK;
+}
+
+int lair_b200_set_option(const char* name, int64_t value) {
+    if (!name) return LAIR_B200_ERR_INVALID;
+    Options& o = g_ctx.opt;
+    if (!strcmp(name, "nb")) {
+        if (value < 32 || value % 32) {
+            set_error("nb must be a positive multiple of 32, got %lld", (long long)value);
+            return LAIR_B200_ERR_INVALID;
+        }
+        o.nb = value;
+    } else if (!strcmp(name, "small_n")) {
+        o.small_n = value;
+    } else if (!strcmp(name, "lookahead")) {
+        o.lookahead = value;
+    } else if (!strcmp(name, "batched_cfg")) {
+        o.batched_cfg = value;
+    } else {
+        set_error("unknown option '%s'", name);
+        return LAIR_B200_ERR_INVALID;
+    }
+    return LAIR_B200_OK;
+}
+
+int lair_b200_get_option(const char* name, int64_t* value) {
+    if (!name || !value) return LAIR_B200_ERR_INVALID;
+    const Options& o = g_ctx.opt;
+    if (!strcmp(name, "nb")) *value = o.nb;
+    else if (!strcmp(name, "small_n")) *value = o.small_n;
+    else if (!strcmp(name, "lookahead")) *value = o.lookahead;
+    else if (!strcmp(name, "batched_cfg")) *value = o.batched_cfg;
+    else {
+        set_error("unknown option '%s'", name);
+        return LAIR_B200_ERR_INVALID;
+    }
+    return LAIR_B200_OK;
+}
+
+int64_t lair_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+// Trailing-matrix update  C -= A * B  (row-major, alpha = -1, no conjugation): the one true
+// contraction of the LU path (reference call site src/lapack/getrf.rs:289-296, routine
+// src/blas/gemm.rs:6-32).  >= 95 % of the flops of a large factorization run here.
+//
+// f64: FP64 tensor cores.  tcgen05.mma has no f64 kind on sm_100a, so the tensor path is
+//      mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the only native DMMA shape on this chip) with
+//      register accumulators; operands are staged global -> shared by a 4-stage cp.async
+//      (LDGSTS) ring, 128x128x16 CTA tiles, 8 warps of 64x32.
+// f32: native FP32 FMA (exactly rounded products, meets the reference's backward error;
+//      a TF32x3 tcgen05 path is the planned replacement), same staging, 8x8 thread tiles.
+//
+// Roofline: tensor/FMA-bound.  Algorithmic flops = 2*M*N*K per launch.
+#include "common.cuh"
+
+namespace lair {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
+
+template <class T> struct Tile {
+    static constexpr int VEC = 16 / sizeof(T);      // elements per 16-byte chunk
+    static constexpr int LDA_S = BK + 4;            // f64: 20 doubles (bank = 8g+2t), f32: 20 floats
+    static constexpr int LDB_S = BN + 4;            // f64: 132 doubles (bank = 8t+2g)
+    static constexpr int A_ELEMS = BM * LDA_S;
+    static constexpr int B_ELEMS = BK * LDB_S;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(T);
+};
+
+// cp.async of `bytes` (0..16) valid source bytes into a 16-byte shared destination; the
+// remainder is zero-filled, so out-of-range tile elements contribute nothing.
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small_zfill(void* smem_dst, const void* gmem_src, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(s), "l"(gmem_src), "n"(BYTES), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Stage loader shared by both precisions.  ALIGNED: every 16-byte chunk is 16-byte aligned
+// in global memory (pointers and leading dimensions multiples of VEC).
+template <class T, bool ALIGNED>
+__device__ __forceinline__ void load_stage(T* __restrict__ sa, T* __restrict__ sb, const T* __restrict__ A, long long lda,
+                                           const T* __restrict__ B, long long ldb, int M, int N, int K, int m0, int n0,
+                                           int k0, int tid) {
+    using TL = Tile<T>;
+    constexpr int VEC = TL::VEC;
+    // A tile: BM rows x BK cols
+    constexpr int A_CPR = BK / VEC;  // chunks per row
+    constexpr int A_CHUNKS = BM * A_CPR;
+#pragma unroll
+    for (int c = tid; c < A_CHUNKS; c += GEMM_THREADS) {
+        int r = c / A_CPR, kc = (c % A_CPR) * VEC;
+        int gr = m0 + r, gk = k0 + kc;
+        int valid = (gr < M) ? (K - gk) : 0;
+        valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
+        const T* src = A + (long long)(gr < M ? gr : 0) * lda + (valid > 0 ? gk : 0);
+        T* dst = sa + r * TL::LDA_S + kc;
+        if (ALIGNED) {
+            cp_async16_zfill(dst, src, valid * (int)sizeof(T));
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                cp_async_small_zfill<sizeof(T)>(dst + e, (e < valid) ? src + e : src, (e < valid) ? (int)sizeof(T) : 0);
+        }
+    }
+    // B tile: BK rows x BN cols
+    constexpr int B_CPR = BN / VEC;
+    constexpr int B_CHUNKS = BK * B_CPR;
+#pragma unroll
+    for (int c = tid; c < B_CHUNKS; c += GEMM_THREADS) {
+        int r = c / B_CPR, nc = (c % B_CPR) * VEC;
+        int gk = k0 + r, gn = n0 + nc;
+        int valid = (gk < K) ? (N - gn) : 0;
+        valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
+        const T* src = B + (long long)(gk < K ? gk : 0) * ldb + (valid > 0 ? gn : 0);
+        T* dst = sb + r * TL::LDB_S + nc;
+        if (ALIGNED) {
+            cp_async16_zfill(dst, src, valid * (int)sizeof(T));
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                cp_async_small_zfill<sizeof(T)>(dst + e, (e < valid) ? src + e : src, (e < valid) ? (int)sizeof(T) : 0);
+        }
+    }
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- f64: DMMA ------------------------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
+                   double* __restrict__ C, long long ldc, int M, int N, int K, int tiles_m) {
+    using TL = Tile<double>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, 64 x 32 each
+    // column-major rasterisation over tiles: consecutive CTAs share the B (U12) tile column
+    const int tile = blockIdx.x;
+    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int KT = (K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage<double, ALIGNED>(smem + s * TL::STAGE_ELEMS, smem + s * TL::STAGE_ELEMS + TL::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0, s * BK, tid);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) {
+                int slot = nk % STAGES;
+                load_stage<double, ALIGNED>(smem + slot * TL::STAGE_ELEMS, smem + slot * TL::STAGE_ELEMS + TL::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0, nk * BK, tid);
+            }
+            cp_async_commit();
+        }
+        const double* sa = smem + (kt % STAGES) * TL::STAGE_ELEMS;
+        const double* sb = sa + TL::A_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = sa[(wm * 64 + i * 8 + g) * TL::LDA_S + kk * 4 + t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = sb[(kk * 4 + t) * TL::LDB_S + wn * 32 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: C -= acc.  Each thread owns (row g, cols 2t, 2t+1) of every 8x8 tile.
+    const bool vec_ok = ALIGNED && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int row = m0 + wm * 64 + i * 8 + g;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int col = n0 + wn * 32 + j * 8 + 2 * t;
+            double* p = C + (long long)row * ldc + col;
+            if (vec_ok && col + 1 < N) {
+                double2 v = *reinterpret_cast<double2*>(p);
+                v.x -= acc[i][j][0];
+                v.y -= acc[i][j][1];
+                *reinterpret_cast<double2*>(p) = v;
+            } else {
+                if (col < N) p[0] -= acc[i][j][0];
+                if (col + 1 < N) p[1] -= acc[i][j][1];
+            }
+        }
+    }
+}
+
+// ---- f32: FFMA, 8x8 register tiles -------------------------------------------------------------
+template <bool ALIGNED>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+sgemm_minus_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
+                   float* __restrict__ C, long long ldc, int M, int N, int K, int tiles_m) {
+    using TL = Tile<float>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // rows ty + 16*i, cols tx*4 + 64*h + e
+    const int tile = blockIdx.x;
+    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int KT = (K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage<float, ALIGNED>(smem + s * TL::STAGE_ELEMS, smem + s * TL::STAGE_ELEMS + TL::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0, s * BK, tid);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) {
+                int slot = nk % STAGES;
+                load_stage<float, ALIGNED>(smem + slot * TL::STAGE_ELEMS, smem + slot * TL::STAGE_ELEMS + TL::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0, nk * BK, tid);
+            }
+            cp_async_commit();
+        }
+        const float* sa = smem + (kt % STAGES) * TL::STAGE_ELEMS;
+        const float* sb = sa + TL::A_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float af[8], bf[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = sa[(ty + 16 * i) * TL::LDA_S + kk];
+            float4 b0 = *reinterpret_cast<const float4*>(sb + kk * TL::LDB_S + tx * 4);
+            float4 b1 = *reinterpret_cast<const float4*>(sb + kk * TL::LDB_S + 64 + tx * 4);
+            bf[0] = b0.x; bf[1] = b0.y; bf[2] = b0.z; bf[3] = b0.w;
+            bf[4] = b1.x; bf[5] = b1.y; bf[6] = b1.z; bf[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+        }
+    }
+    cp_async_wait<0>();
+    const bool vec_ok = ALIGNED && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int row = m0 + ty + 16 * i;
+        if (row >= M) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int col = n0 + h * 64 + tx * 4;
+            float* p = C + (long long)row * ldc + col;
+            if (vec_ok && col + 3 < N) {
+                float4 v = *reinterpret_cast<float4*>(p);
+                v.x -= acc[i][h * 4 + 0];
+                v.y -= acc[i][h * 4 + 1];
+                v.z -= acc[i][h * 4 + 2];
+                v.w -= acc[i][h * 4 + 3];
+                *reinterpret_cast<float4*>(p) = v;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (col + e < N) p[e] -= acc[i][h * 4 + e];
+            }
+        }
+    }
+}
+
+template <class T> struct GemmKernel;
+template <> struct GemmKernel<double> {
+    template <bool AL> static auto get() { return dgemm_minus_kernel<AL>; }
+};
+template <> struct GemmKernel<float> {
+    template <bool AL> static auto get() { return sgemm_minus_kernel<AL>; }
+};
+
+template <class T, bool AL>
+int launch_gemm(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, const T* d_b, int64_t ldb, T* d_c, int64_t ldc,
+                cudaStream_t s) {
+    auto kern = GemmKernel<T>::template get<AL>();
+    static bool configured = false;
+    if (!configured) {
+        LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<T>::SMEM_BYTES));
+        configured = true;
+    }
+    int64_t tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+    int64_t tiles = tiles_m * tiles_n;
+    LAIR_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
+    kern<<<(unsigned)tiles, GEMM_THREADS, Tile<T>::SMEM_BYTES, s>>>(d_a, (long long)lda, d_b, (long long)ldb, d_c, (long long)ldc, (int)m,
+                                                                  (int)n, (int)k, (int)tiles_m);
+    LAIR_LAUNCH_CHECK();
+    return LAIR_B200_OK;
+}
+
+}  // namespace
+
+template <class T>
+int gemm_minus_dev(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, const T* d_b, int64_t ldb, T* d_c, int64_t ldc,
+                   cudaStream_t s) {
+    LAIR_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative dimension");
+    LAIR_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "gemm: dimension too large");
+    if (m == 0 || n == 0 || k == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(lda >= k && ldb >= n && ldc >= n, "gemm: leading dimension too small");
+    constexpr int VEC = 16 / sizeof(T);
+    const bool aligned = (lda % VEC == 0) && (ldb % VEC == 0) && (reinterpret_cast<uintptr_t>(d_a) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(d_b) % 16 == 0);
+    if (aligned) return launch_gemm<T, true>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);
+    return launch_gemm<T, false>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);
+}
+
+template int gemm_minus_dev<float>(int64_t, int64_t, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, cudaStream_t);
+template int gemm_minus_dev<double>(int64_t, int64_t, int64_t, const double*, int64_t, const double*, int64_t, double*, int64_t, cudaStream_t);
+
+}  // namespace lair

@@ -1,0 +1,195 @@
+"""One-shot GPU probe: ceilings (cuBLAS DGEMM via torch), this library's kernels in isolation,
+and whole getrf/getrs at several sizes.  Prints JSON lines; run under gpurun and keep the log
+in gpurun_out/ (summaries are copied to profiles/ by hand).
+
+    python tools/gpu_probe.py [section ...]     sections: ceil gemm batched panel getrf getrs
+"""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lair_b200 import _ffi  # noqa: E402
+
+L = _ffi.lib()
+STREAM = None
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def timeit(fn, reps=5, warm=2, setup=None):
+    for _ in range(warm):
+        if setup:
+            setup()
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if setup:
+            setup()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), float(np.median(ts))
+
+
+def out(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def sec_ceil():
+    for n in (4096, 8192):
+        a = torch.rand(n, n, dtype=torch.float64, device="cuda")
+        b = torch.rand(n, n, dtype=torch.float64, device="cuda")
+        c = torch.empty_like(a)
+        best, med = timeit(lambda: torch.matmul(a, b, out=c), reps=5)
+        out(bench="cublas_dgemm", n=n, ms_best=best, ms_med=med, tflops_best=2 * n ** 3 / best * 1e-9, tflops_med=2 * n ** 3 / med * 1e-9)
+    n = 8192
+    a = torch.rand(n, 256, dtype=torch.float64, device="cuda")
+    b = torch.rand(256, n, dtype=torch.float64, device="cuda")
+    c = torch.rand(n, n, dtype=torch.float64, device="cuda")
+    best, med = timeit(lambda: torch.addmm(c, a, b, alpha=-1.0, out=c), reps=5)
+    out(bench="cublas_dgemm_rank256", n=n, ms_best=best, tflops_best=2 * n * n * 256 / best * 1e-9)
+    for n in (8192,):
+        a = torch.rand(n, n, dtype=torch.float32, device="cuda")
+        b = torch.rand(n, n, dtype=torch.float32, device="cuda")
+        torch.backends.cuda.matmul.allow_tf32 = False
+        best, med = timeit(lambda: torch.matmul(a, b), reps=5)
+        out(bench="cublas_sgemm_fp32", n=n, ms_best=best, tflops_best=2 * n ** 3 / best * 1e-9)
+    # sustained DGEMM for ~3 s with clocks
+    n = 8192
+    a = torch.rand(n, n, dtype=torch.float64, device="cuda")
+    b = torch.rand(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 0
+    while time.time() - t0 < 3.0:
+        for _ in range(4):
+            torch.matmul(a, b, out=c)
+        reps += 4
+        torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out(bench="cublas_dgemm_sustained", n=n, reps=reps, tflops=2 * n ** 3 * reps / ms * 1e-9)
+    # torch LU (cuSOLVER getrf) as a library reference point
+    for n in (4096, 8192):
+        a = torch.rand(n, n, dtype=torch.float64, device="cuda") * 10
+        best, med = timeit(lambda: torch.linalg.lu_factor(a), reps=3, warm=1)
+        out(bench="cusolver_dgetrf_via_torch", n=n, ms_best=best, tflops=2 / 3 * n ** 3 / best * 1e-9)
+
+
+def sec_gemm():
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}gemm_minus_dev")
+        for (m, n, k) in ((8192, 8192, 256), (8192, 8192, 128), (8192, 8192, 32), (4096, 4096, 256), (2048, 2048, 256),
+                          (8192, 128, 128), (8192, 64, 64), (8192, 32, 32), (8192, 64, 256)):
+            a = torch.rand(m, k, dtype=dt, device="cuda")
+            b = torch.rand(k, n, dtype=dt, device="cuda")
+            c = torch.rand(m, n, dtype=dt, device="cuda")
+            best, med = timeit(lambda: _ffi.check(fn(m, n, k, a.data_ptr(), k, b.data_ptr(), n, c.data_ptr(), n, stream())), reps=5)
+            out(bench=f"{pfx}gemm_minus", m=m, n=n, k=k, ms_best=best, ms_med=med, tflops_best=2 * m * n * k / best * 1e-9)
+
+
+def sec_batched():
+    batch = 1_000_000
+    for dt, pfx, bpm in ((torch.float64, "d", 16512), (torch.float32, "s", 8320)):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_batched_dev")
+        a0 = torch.rand(batch, 32, 32, dtype=dt, device="cuda") * 10
+        a = a0.clone()
+        ipiv = torch.empty(batch, 32, dtype=torch.int32, device="cuda")
+        info = torch.empty(batch, dtype=torch.int32, device="cuda")
+        for cfg in (0, 1):
+            _ffi.set_option("batched_cfg", cfg)
+            best, med = timeit(lambda: _ffi.check(fn(batch, 32, a.data_ptr(), ipiv.data_ptr(), info.data_ptr(), stream())),
+                               reps=5, setup=lambda: a.copy_(a0))
+            out(bench=f"{pfx}getrf_batched32", cfg=cfg, batch=batch, ms_best=best, ms_med=med, mats_per_s=batch / best * 1e3,
+                gbs=batch * bpm / best * 1e-6, frac_of_6453=batch * bpm / best * 1e-6 / 6453.7)
+        _ffi.set_option("batched_cfg", 0)
+
+
+def sec_panel():
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for m in (1024, 4096, 8192, 16384, 65536):
+            w = 32
+            a0 = torch.rand(m, w, dtype=dt, device="cuda")
+            a = a0.clone()
+            ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
+            info = torch.empty(1, dtype=torch.int32, device="cuda")
+            best, med = timeit(lambda: _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
+                               setup=lambda: a.copy_(a0))
+            out(bench=f"{pfx}panel", m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
+
+
+def sec_getrf():
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for n in (1024, 2048, 4096, 8192):
+            for nb in (128, 256, 512):
+                _ffi.set_option("nb", nb)
+                a0 = torch.rand(n, n, dtype=dt, device="cuda") * 10
+                a = a0.clone()
+                ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+                info = torch.empty(1, dtype=torch.int32, device="cuda")
+                l0 = _ffi.launch_count()
+                best, med = timeit(lambda: _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream())),
+                                   reps=3, warm=1, setup=lambda: a.copy_(a0))
+                launches = (_ffi.launch_count() - l0) // 4
+                # backward error on device
+                perm = torch.arange(n, device="cuda")
+                piv = ipiv.cpu().numpy()
+                pn = np.arange(n)
+                for i, p in enumerate(piv):
+                    if i != p:
+                        pn[i], pn[p] = pn[p], pn[i]
+                PA = a0.double()[torch.from_numpy(pn).cuda()]
+                LU = a.double()
+                rec = (torch.tril(LU, -1) + torch.eye(n, dtype=torch.float64, device="cuda")) @ torch.triu(LU)
+                eps = (2.0 ** -53) if dt == torch.float64 else (2.0 ** -24)
+                be = float(torch.linalg.norm(PA - rec) / (n * eps * torch.linalg.norm(PA)))
+                out(bench=f"{pfx}getrf", n=n, nb=nb, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9, launches=launches,
+                    backward_error=be, info=int(info.item()))
+        _ffi.set_option("nb", 256)
+
+
+def sec_getrs():
+    for dt, pfx in ((torch.float64, "d"),):
+        n, nrhs = 8192, 64
+        a0 = torch.rand(n, n, dtype=dt, device="cuda") * 10
+        a = a0.clone()
+        ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+        info = torch.empty(1, dtype=torch.int32, device="cuda")
+        _ffi.check(getattr(L, f"lair_b200_{pfx}getrf_dev")(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream()))
+        b0 = torch.rand(n, nrhs, dtype=dt, device="cuda")
+        b = b0.clone()
+        fn = getattr(L, f"lair_b200_{pfx}getrs_dev")
+        l0 = _ffi.launch_count()
+        best, med = timeit(lambda: _ffi.check(fn(n, nrhs, a.data_ptr(), n, ipiv.data_ptr(), b.data_ptr(), nrhs, stream())), reps=3, warm=1,
+                           setup=lambda: b.copy_(b0))
+        launches = (_ffi.launch_count() - l0) // 4
+        res = float(torch.linalg.norm(a0 @ b - b0) / (torch.linalg.norm(a0) * torch.linalg.norm(b) * n * 2.0 ** -53))
+        out(bench=f"{pfx}getrs", n=n, nrhs=nrhs, ms_best=best, launches=launches, tflops=2 * n * n * nrhs / best * 1e-9, residual=res)
+
+
+if __name__ == "__main__":
+    secs = sys.argv[1:] or ["ceil", "gemm", "batched", "panel", "getrf", "getrs"]
+    out(device=torch.cuda.get_device_name(0), torch=torch.__version__)
+    for s in secs:
+        try:
+            globals()[f"sec_{s}"]()
+        except Exception as e:  # keep going: one broken section must not hide the others
+            out(section=s, error=repr(e))
