@@ -133,6 +133,13 @@ LAIR_B200_API int lair_b200_set_option(const char* name, int64_t value);
 LAIR_B200_API int lair_b200_get_option(const char* name, int64_t* value);
 /* Number of kernels this library has launched since init (for gpu_launches accounting). */
 LAIR_B200_API int64_t lair_b200_launch_count(void);
+/* Optional live timing of kernel families with CUDA events on the launching stream:
+ * begin() arms it, end() synchronises and accumulates, get() returns for one family
+ * ("gemm", "panel", "laswp", "trsm", "batched", "small") the summed device time (ms), the
+ * number of launches and their algorithmic work (flops for gemm/trsm/small, bytes otherwise). */
+LAIR_B200_API int lair_b200_profile_begin(void);
+LAIR_B200_API int lair_b200_profile_end(void);
+LAIR_B200_API int lair_b200_profile_get(const char* family, double* ms, int64_t* launches, double* work);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,10 @@ _SIGNATURES = {
     "lair_b200_set_option": [ctypes.c_char_p, i64],
     "lair_b200_get_option": [ctypes.c_char_p, ctypes.POINTER(i64)],
     "lair_b200_launch_count": [],
+    "lair_b200_profile_begin": [],
+    "lair_b200_profile_end": [],
+    "lair_b200_profile_get": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
+                              ctypes.POINTER(ctypes.c_double)],
 }
 for _p in "sdcz":
     _SIGNATURES[f"lair_b200_{_p}getrf"] = [i64, i64, vp, i64, i64, vp, vp]
@@ -88,6 +92,21 @@ def get_option(name: str) -> int:
 
 def launch_count() -> int:
     return int(lib().lair_b200_launch_count())
+
+
+def profile_begin() -> None:
+    check(lib().lair_b200_profile_begin())
+
+
+def profile_end() -> dict:
+    """Stop live kernel timing; returns {family: {"ms", "launches", "work"}}."""
+    check(lib().lair_b200_profile_end())
+    out = {}
+    for fam in ("gemm", "panel", "laswp", "trsm", "batched", "small"):
+        ms, n, w = ctypes.c_double(0), i64(0), ctypes.c_double(0)
+        check(lib().lair_b200_profile_get(fam.encode(), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(w)))
+        out[fam] = {"ms": ms.value, "launches": int(n.value), "work": w.value}
+    return out
 
 
 def device_count() -> int:

@@ -176,6 +176,7 @@ int launch_batched(long long batch, int n, T* d_a, int32_t* d_ipiv, int32_t* d_i
     long long cap = (long long)ctx().sm_count * blocks_per_sm;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) return LAIR_B200_OK;
+    ProfScope prof(kProfBatched, s, (double)batch * (2.0 * n * n * sizeof(T) + 4.0 * n));
     kern<<<grid, WARPS * 32, smem, s>>>(d_a, d_ipiv, d_info, batch, n);
     LAIR_LAUNCH_CHECK();
     return LAIR_B200_OK;

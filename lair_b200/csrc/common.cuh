@@ -46,6 +46,25 @@ void count_launch(int n = 1);
         LAIR_CUDA_CHECK(cudaGetLastError());     \
     } while (0)
 
+// ---- optional per-kernel-family timing (profile.cu) -----------------------------------------
+enum ProfBucket { kProfGemm = 0, kProfPanel, kProfLaswp, kProfTrsm, kProfBatched, kProfSmall, kProfOther, kProfBuckets };
+bool prof_enabled();
+// Brackets the launches issued in its scope with CUDA events on `s`; `work` = algorithmic
+// flops (gemm, trsm) or bytes (laswp, panel, batched) of those launches.
+class ProfScope {
+public:
+    ProfScope(int bucket, cudaStream_t s, double work);
+    ~ProfScope();
+    ProfScope(const ProfScope&) = delete;
+    ProfScope& operator=(const ProfScope&) = delete;
+
+private:
+    int bucket_;
+    cudaStream_t stream_;
+    double work_;
+    cudaEvent_t e0_;
+};
+
 // ---- scalar layer: exact (never FMA-contracted) arithmetic ------------------------------
 // The reference is Rust: `a -= l * u` is a rounded multiply followed by a rounded
 // subtract (src/lapack/getrf.rs:86-87).  The *_rn intrinsics are never contracted by

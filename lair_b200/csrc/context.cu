@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "host_io.cuh"
 
 namespace lair {
 
@@ -148,6 +149,7 @@ int lair_b200_shutdown(void) {
         if (ev) cudaEventDestroy(ev);
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
+    pool().release();
     c = Context();
     return LAIR_B200_OK;
 }

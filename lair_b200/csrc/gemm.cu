@@ -271,6 +271,7 @@ int launch_gemm(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, cons
     int64_t tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
     int64_t tiles = tiles_m * tiles_n;
     LAIR_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
+    ProfScope prof(kProfGemm, s, 2.0 * (double)m * (double)n * (double)k);
     kern<<<(unsigned)tiles, GEMM_THREADS, Tile<T>::SMEM_BYTES, s>>>(d_a, (long long)lda, d_b, (long long)ldb, d_c, (long long)ldc, (int)m,
                                                                   (int)n, (int)k, (int)tiles_m);
     LAIR_LAUNCH_CHECK();

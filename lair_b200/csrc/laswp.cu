@@ -100,6 +100,8 @@ int launch_laswp(int ncols, T* d_a, int64_t lda, int k0, int k1, const int32_t* 
         configured = maxb;
     }
     unsigned grid = (unsigned)((ncols + 32 * VEC - 1) / (32 * VEC));
+    // upper bound on moved rows: 2 per interchange, each read once and written once
+    ProfScope prof(kProfLaswp, s, 4.0 * (double)(k1 - k0) * (double)ncols * sizeof(T));
     kern<<<grid, LASWP_THREADS, smem, s>>>(d_a, (long long)lda, ncols, k0, k1, d_ipiv);
     LAIR_LAUNCH_CHECK();
     return LAIR_B200_OK;

@@ -304,6 +304,7 @@ struct PanelVariant {
         const int grid = (int)((rows + per_cta - 1) / per_cta);
         uint4* ws = reinterpret_cast<uint4*>(c.panel_ws);
         int* err = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(c.panel_ws) + PANEL_WS_BYTES - 256);
+        ProfScope prof(kProfPanel, s, 2.0 * (double)rows * (double)w * sizeof(T));
         panel_kernel<T, W, RPT, MINB><<<grid, PANEL_TPB, 0, s>>>(d_a, (long long)lda, (int)rows, (int)w, d_ipiv, row_base, d_info,
                                                                  step_base, ws, c.panel_seq, err);
         c.panel_seq += 64;

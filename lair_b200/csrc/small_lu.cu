@@ -209,6 +209,7 @@ int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, 
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         configured = limit;
     }
+    ProfScope prof(kProfSmall, s, 2.0 / 3.0 * (double)m * (double)n * (double)(m < n ? m : n));
     kern<<<1, kSmallThreads, smem, s>>>(d_a, (long long)lda, (int)m, (int)n, d_ipiv, d_info, use_smem, ldw,
                                         std_layout ? 1 : 0);
     LAIR_LAUNCH_CHECK();

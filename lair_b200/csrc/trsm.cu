@@ -83,6 +83,7 @@ int trsm_lower_unit_dev(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* 
     if (k <= 1 || ncols == 0) return LAIR_B200_OK;
     if (k <= TB) {
         unsigned grid = (unsigned)((ncols + TRSM_THREADS - 1) / TRSM_THREADS);
+        ProfScope prof(kProfTrsm, s, (double)k * (double)k * (double)ncols);
         trsm_lower_unit32_kernel<T><<<grid, TRSM_THREADS, 0, s>>>(d_l, (long long)ldl, d_b, (long long)ldb, (int)k, (int)ncols);
         LAIR_LAUNCH_CHECK();
         return LAIR_B200_OK;
@@ -100,6 +101,7 @@ int trsm_upper_dev(int64_t k, int64_t ncols, const T* d_u, int64_t ldu, T* d_b, 
     if (k == 0 || ncols == 0) return LAIR_B200_OK;
     if (k <= TB) {
         unsigned grid = (unsigned)((ncols + TRSM_THREADS - 1) / TRSM_THREADS);
+        ProfScope prof(kProfTrsm, s, (double)k * (double)k * (double)ncols);
         trsm_upper32_kernel<T><<<grid, TRSM_THREADS, 0, s>>>(d_u, (long long)ldu, d_b, (long long)ldb, (int)k, (int)ncols);
         LAIR_LAUNCH_CHECK();
         return LAIR_B200_OK;
