@@ -134,6 +134,8 @@ struct Options {
     int64_t small_n = 128;   // max(m, n) handled by the single-CTA exact kernel
     int64_t lookahead = 1;   // overlap panel k+1 with trailing update k
     int64_t batched_cfg = 0; // occupancy variant of the batched kernel (batched_lu.cu)
+    int64_t panel_cluster = 1;  // use the single-cluster DSMEM panel kernel when the panel fits
+    int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
 };
 
 struct Context {
@@ -169,10 +171,14 @@ template <class T> int laswp_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0,
 template <class T> int trsm_lower_unit_dev(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int trsm_upper_dev(int64_t k, int64_t ncols, const T* d_u, int64_t ldu, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int gemm_minus_dev(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, const T* d_b, int64_t ldb, T* d_c, int64_t ldc, cudaStream_t s);
+template <> int gemm_minus_dev<double>(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, const double* d_b, int64_t ldb, double* d_c, int64_t ldc, cudaStream_t s);  // gemm_f64.cu
 // factor the (rows x w) panel at d_a (w <= panel width limit) with partial pivoting;
 // d_ipiv[0..w) receive row indices relative to d_a's row 0 plus `row_base`.
 template <class T> int panel_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 template <class T> int panel_max_width(int64_t rows);
+// single-cluster DSMEM variant (panel_cluster.cu); LAIR_B200_ERR_UNSUPPORTED when it does not fit
+template <class T> int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
+int panel_cluster_max_rows();
 // 1 if a panel exchange timed out since the last clear (results are then invalid)
 int panel_error_flag(bool clear);
 

@@ -169,6 +169,10 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.lookahead = value;
     } else if (!strcmp(name, "batched_cfg")) {
         o.batched_cfg = value;
+    } else if (!strcmp(name, "panel_cluster")) {
+        o.panel_cluster = value;
+    } else if (!strcmp(name, "gemm_cfg")) {
+        o.gemm_cfg = value;
     } else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;
@@ -183,6 +187,8 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "small_n")) *value = o.small_n;
     else if (!strcmp(name, "lookahead")) *value = o.lookahead;
     else if (!strcmp(name, "batched_cfg")) *value = o.batched_cfg;
+    else if (!strcmp(name, "panel_cluster")) *value = o.panel_cluster;
+    else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
     else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;

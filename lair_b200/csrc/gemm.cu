@@ -1,15 +1,10 @@
-// Trailing-matrix update  C -= A * B  (row-major, alpha = -1, no conjugation): the one true
-// contraction of the LU path (reference call site src/lapack/getrf.rs:289-296, routine
-// src/blas/gemm.rs:6-32).  >= 95 % of the flops of a large factorization run here.
+// f32 trailing-matrix update  C -= A * B  (row-major, alpha = -1, no conjugation); the f64
+// tensor-core version lives in gemm_f64.cu.  Reference call site src/lapack/getrf.rs:289-296,
+// routine src/blas/gemm.rs:6-32.
 //
-// f64: FP64 tensor cores.  tcgen05.mma has no f64 kind on sm_100a, so the tensor path is
-//      mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the only native DMMA shape on this chip) with
-//      register accumulators; operands are staged global -> shared by a 4-stage cp.async
-//      (LDGSTS) ring, 128x128x16 CTA tiles, 8 warps of 64x32.
-// f32: native FP32 FMA (exactly rounded products, meets the reference's backward error;
-//      a TF32x3 tcgen05 path is the planned replacement), same staging, 8x8 thread tiles.
-//
-// Roofline: tensor/FMA-bound.  Algorithmic flops = 2*M*N*K per launch.
+// Native FP32 FMA (exactly rounded products, meets the reference's backward error; a TF32x3
+// tcgen05 path is the planned replacement): 128x128x16 CTA tiles staged by a 4-stage cp.async
+// ring, 8x8 register tiles per thread.  Roofline: FP32-FMA-bound; flops = 2*M*N*K per launch.
 #include "common.cuh"
 
 namespace lair {
@@ -85,89 +80,6 @@ __device__ __forceinline__ void load_stage(T* __restrict__ sa, T* __restrict__ s
 #pragma unroll
             for (int e = 0; e < VEC; ++e)
                 cp_async_small_zfill<sizeof(T)>(dst + e, (e < valid) ? src + e : src, (e < valid) ? (int)sizeof(T) : 0);
-        }
-    }
-}
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-// ---- f64: DMMA ------------------------------------------------------------------------------
-template <bool ALIGNED>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
-                   double* __restrict__ C, long long ldc, int M, int N, int K, int tiles_m) {
-    using TL = Tile<double>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* smem = reinterpret_cast<double*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, 64 x 32 each
-    // column-major rasterisation over tiles: consecutive CTAs share the B (U12) tile column
-    const int tile = blockIdx.x;
-    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-
-    double acc[8][4][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    const int KT = (K + BK - 1) / BK;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) load_stage<double, ALIGNED>(smem + s * TL::STAGE_ELEMS, smem + s * TL::STAGE_ELEMS + TL::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0, s * BK, tid);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < KT) {
-                int slot = nk % STAGES;
-                load_stage<double, ALIGNED>(smem + slot * TL::STAGE_ELEMS, smem + slot * TL::STAGE_ELEMS + TL::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0, nk * BK, tid);
-            }
-            cp_async_commit();
-        }
-        const double* sa = smem + (kt % STAGES) * TL::STAGE_ELEMS;
-        const double* sb = sa + TL::A_ELEMS;
-#pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            double af[8], bf[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = sa[(wm * 64 + i * 8 + g) * TL::LDA_S + kk * 4 + t];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = sb[(kk * 4 + t) * TL::LDB_S + wn * 32 + j * 8 + g];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-    }
-    cp_async_wait<0>();
-    // epilogue: C -= acc.  Each thread owns (row g, cols 2t, 2t+1) of every 8x8 tile.
-    const bool vec_ok = ALIGNED && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int row = m0 + wm * 64 + i * 8 + g;
-        if (row >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int col = n0 + wn * 32 + j * 8 + 2 * t;
-            double* p = C + (long long)row * ldc + col;
-            if (vec_ok && col + 1 < N) {
-                double2 v = *reinterpret_cast<double2*>(p);
-                v.x -= acc[i][j][0];
-                v.y -= acc[i][j][1];
-                *reinterpret_cast<double2*>(p) = v;
-            } else {
-                if (col < N) p[0] -= acc[i][j][0];
-                if (col + 1 < N) p[1] -= acc[i][j][1];
-            }
         }
     }
 }
@@ -252,9 +164,6 @@ sgemm_minus_kernel(const float* __restrict__ A, long long lda, const float* __re
 }
 
 template <class T> struct GemmKernel;
-template <> struct GemmKernel<double> {
-    template <bool AL> static auto get() { return dgemm_minus_kernel<AL>; }
-};
 template <> struct GemmKernel<float> {
     template <bool AL> static auto get() { return sgemm_minus_kernel<AL>; }
 };
@@ -295,6 +204,5 @@ int gemm_minus_dev(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, c
 }
 
 template int gemm_minus_dev<float>(int64_t, int64_t, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, cudaStream_t);
-template int gemm_minus_dev<double>(int64_t, int64_t, int64_t, const double*, int64_t, const double*, int64_t, double*, int64_t, cudaStream_t);
 
 }  // namespace lair

@@ -1,0 +1,236 @@
+// f64 trailing-matrix update  C -= A * B  (row-major): the one true contraction of the LU
+// path (reference call site src/lapack/getrf.rs:289-296, routine src/blas/gemm.rs:6-32).
+//
+// FP64 tensor cores: tcgen05.mma has no f64 kind on sm_100a, so the tensor path is
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 -- the only native DMMA shape on this chip; measured
+// issue-rate peak 37.0 TFLOP/s, profiles/r1_microbench_fp64_peak.jsonl) with register
+// accumulators.  Operands are staged global -> shared with a cp.async (LDGSTS) ring whose
+// row pitches (BK+4, BN+4 doubles) make every 64-bit fragment load bank-conflict free.
+//
+// Tile configurations (template): CTA tile = (WARPS_M*WTM*8) x (WARPS_N*WTN*8), BK = 16.
+//   big    128 x 64, 4 warps of 64x32: two CTAs per SM, so one CTA's prologue/epilogue hides
+//          under the other's DMMA main loop;
+//   skinny  64 x 32, 2 warps of 32x32: panel-internal and multi-RHS updates with N <= 64,
+//          where the big tile would leave most SMs idle.
+// The accumulators start at -C (loaded before the main loop, overlapping the first operand
+// loads), so the epilogue is a pure store of -(acc) = C - A*B.
+// Roofline: tensor-bound; algorithmic flops = 2*M*N*K per launch.
+#include "common.cuh"
+
+namespace lair {
+namespace {
+
+constexpr int BK = 16;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gmem_src, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int WARPS_M, int WARPS_N, int WTM, int WTN, int STAGES_>
+struct Cfg {
+    static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+    static constexpr int BM = WARPS_M * WTM * 8, BN = WARPS_N * WTN * 8;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int LDA_S = BK + 4;  // doubles: fragment bank = 8g + 2t
+    static constexpr int LDB_S = BN + 4;  // doubles: fragment bank = 8t + 2g
+    static constexpr int A_ELEMS = BM * LDA_S, B_ELEMS = BK * LDB_S;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+};
+
+template <class C, bool ALIGNED>
+__device__ __forceinline__ void load_stage(double* __restrict__ sa, double* __restrict__ sb, const double* __restrict__ A,
+                                           long long lda, const double* __restrict__ B, long long ldb, int M, int N, int K,
+                                           int m0, int n0, int k0, int tid) {
+    constexpr int A_CPR = BK / 2, A_CHUNKS = C::BM * A_CPR;
+#pragma unroll
+    for (int c = tid; c < A_CHUNKS; c += C::THREADS) {
+        const int r = c / A_CPR, kc = (c % A_CPR) * 2;
+        const int gr = m0 + r, gk = k0 + kc;
+        int valid = (gr < M) ? (K - gk) : 0;
+        valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
+        const double* src = A + (long long)(gr < M ? gr : 0) * lda + (valid > 0 ? gk : 0);
+        double* dst = sa + r * C::LDA_S + kc;
+        if (ALIGNED) {
+            cp_async16_zfill(dst, src, valid * 8);
+        } else {
+            cp_async8_zfill(dst, src, valid > 0 ? 8 : 0);
+            cp_async8_zfill(dst + 1, valid > 1 ? src + 1 : src, valid > 1 ? 8 : 0);
+        }
+    }
+    constexpr int B_CPR = C::BN / 2, B_CHUNKS = BK * B_CPR;
+#pragma unroll
+    for (int c = tid; c < B_CHUNKS; c += C::THREADS) {
+        const int r = c / B_CPR, nc = (c % B_CPR) * 2;
+        const int gk = k0 + r, gn = n0 + nc;
+        int valid = (gk < K) ? (N - gn) : 0;
+        valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
+        const double* src = B + (long long)(gk < K ? gk : 0) * ldb + (valid > 0 ? gn : 0);
+        double* dst = sb + r * C::LDB_S + nc;
+        if (ALIGNED) {
+            cp_async16_zfill(dst, src, valid * 8);
+        } else {
+            cp_async8_zfill(dst, src, valid > 0 ? 8 : 0);
+            cp_async8_zfill(dst + 1, valid > 1 ? src + 1 : src, valid > 1 ? 8 : 0);
+        }
+    }
+}
+
+template <class C, int WARPS_M, int WARPS_N, int WTM, int WTN, int MINB, bool ALIGNED>
+__global__ void __launch_bounds__(C::THREADS, MINB)
+dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
+                   double* __restrict__ Cm, long long ldc, int M, int N, int K, int tiles_m) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    // tiles walk down M first: consecutive CTAs share the B (U12) tile column in L2
+    const int tile = blockIdx.x;
+    const int m0 = (tile % tiles_m) * C::BM, n0 = (tile / tiles_m) * C::BN;
+    const int KT = (K + BK - 1) / BK;
+
+    // operand pipeline first, so the C loads below overlap it
+#pragma unroll
+    for (int s = 0; s < C::STAGES - 1; ++s) {
+        if (s < KT)
+            load_stage<C, ALIGNED>(smem + s * C::STAGE_ELEMS, smem + s * C::STAGE_ELEMS + C::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0,
+                                   s * BK, tid);
+        cp_async_commit();
+    }
+
+    // accumulators start at -C: each thread owns (row g, cols 2t, 2t+1) of every 8x8 tile
+    double acc[WTM][WTN][2];
+    const bool vec_ok = ALIGNED && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cm) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < WTM; ++i) {
+        const int row = m0 + (wm * WTM + i) * 8 + g;
+#pragma unroll
+        for (int j = 0; j < WTN; ++j) {
+            const int col = n0 + (wn * WTN + j) * 8 + 2 * t;
+            double c0 = 0.0, c1 = 0.0;
+            if (row < M) {
+                const double* p = Cm + (long long)row * ldc + col;
+                if (vec_ok && col + 1 < N) {
+                    const double2 v = *reinterpret_cast<const double2*>(p);
+                    c0 = v.x;
+                    c1 = v.y;
+                } else {
+                    if (col < N) c0 = p[0];
+                    if (col + 1 < N) c1 = p[1];
+                }
+            }
+            acc[i][j][0] = -c0;
+            acc[i][j][1] = -c1;
+        }
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<C::STAGES - 2>();
+        __syncthreads();
+        {
+            const int nk = kt + C::STAGES - 1;
+            if (nk < KT) {
+                const int slot = nk % C::STAGES;
+                load_stage<C, ALIGNED>(smem + slot * C::STAGE_ELEMS, smem + slot * C::STAGE_ELEMS + C::A_ELEMS, A, lda, B, ldb, M, N, K,
+                                       m0, n0, nk * BK, tid);
+            }
+            cp_async_commit();
+        }
+        const double* sa = smem + (kt % C::STAGES) * C::STAGE_ELEMS;
+        const double* sb = sa + C::A_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double af[WTM], bf[WTN];
+#pragma unroll
+            for (int i = 0; i < WTM; ++i) af[i] = sa[((wm * WTM + i) * 8 + g) * C::LDA_S + kk * 4 + t];
+#pragma unroll
+            for (int j = 0; j < WTN; ++j) bf[j] = sb[(kk * 4 + t) * C::LDB_S + (wn * WTN + j) * 8 + g];
+#pragma unroll
+            for (int i = 0; i < WTM; ++i)
+#pragma unroll
+                for (int j = 0; j < WTN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C = -(acc)
+#pragma unroll
+    for (int i = 0; i < WTM; ++i) {
+        const int row = m0 + (wm * WTM + i) * 8 + g;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < WTN; ++j) {
+            const int col = n0 + (wn * WTN + j) * 8 + 2 * t;
+            double* p = Cm + (long long)row * ldc + col;
+            if (vec_ok && col + 1 < N) {
+                *reinterpret_cast<double2*>(p) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+            } else {
+                if (col < N) p[0] = -acc[i][j][0];
+                if (col + 1 < N) p[1] = -acc[i][j][1];
+            }
+        }
+    }
+}
+
+template <int WARPS_M, int WARPS_N, int WTM, int WTN, int STAGES_, int MINB, bool AL>
+int launch(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, const double* d_b, int64_t ldb, double* d_c,
+           int64_t ldc, cudaStream_t s) {
+    using C = Cfg<WARPS_M, WARPS_N, WTM, WTN, STAGES_>;
+    auto kern = dgemm_minus_kernel<C, WARPS_M, WARPS_N, WTM, WTN, MINB, AL>;
+    static bool configured = false;
+    if (!configured) {
+        LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t tiles_m = (m + C::BM - 1) / C::BM, tiles_n = (n + C::BN - 1) / C::BN;
+    const int64_t tiles = tiles_m * tiles_n;
+    LAIR_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
+    ProfScope prof(kProfGemm, s, 2.0 * (double)m * (double)n * (double)k);
+    kern<<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(d_a, (long long)lda, d_b, (long long)ldb, d_c, (long long)ldc, (int)m, (int)n,
+                                                           (int)k, (int)tiles_m);
+    LAIR_LAUNCH_CHECK();
+    return LAIR_B200_OK;
+}
+
+template <bool AL>
+int dispatch(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, const double* d_b, int64_t ldb, double* d_c,
+             int64_t ldc, cudaStream_t s) {
+    const int64_t cfg = ctx().opt.gemm_cfg;
+    // tiles of the big configuration; if they cannot fill the SMs twice over, go skinny
+    const int64_t big_tiles = ((m + 127) / 128) * ((n + 63) / 64);
+    const bool skinny = (cfg == 2) || (cfg == 0 && (n <= 32 || big_tiles < 2 * (int64_t)ctx().sm_count));
+    if (skinny) return launch<2, 1, 4, 4, 3, 4, AL>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);   // 64 x 32, 64 threads
+    if (cfg == 3) return launch<2, 4, 8, 4, 4, 1, AL>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s); // 128 x 128, 256 threads, 1 CTA/SM
+    return launch<2, 2, 8, 4, 3, 2, AL>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);               // 128 x 64, 128 threads, 2 CTAs/SM
+}
+
+}  // namespace
+
+template <>
+int gemm_minus_dev<double>(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, const double* d_b, int64_t ldb,
+                           double* d_c, int64_t ldc, cudaStream_t s) {
+    LAIR_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative dimension");
+    LAIR_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "gemm: dimension too large");
+    if (m == 0 || n == 0 || k == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(lda >= k && ldb >= n && ldc >= n, "gemm: leading dimension too small");
+    const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) && (reinterpret_cast<uintptr_t>(d_a) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(d_b) % 16 == 0);
+    if (aligned) return dispatch<true>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);
+    return dispatch<false>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);
+}
+
+}  // namespace lair

@@ -1,0 +1,246 @@
+// Panel factorization for panels of up to 16 x 512 = 8192 rows: ONE thread-block cluster,
+// candidate exchange over distributed shared memory (DSMEM) instead of global memory.
+//
+// Same register-resident, logical-interchange scheme as panel.cu (one matrix row of W
+// columns per thread), but the per-column grid-wide exchange -- the latency that bounds
+// the whole factorization -- never leaves the SMs:
+//   thread candidate -> warp arg-max (REDUX) -> CTA candidate ->
+//   every CTA PUSHES its candidate (|pivot| key, position, reciprocal, full row) into the
+//   shared memory of all CTAs of the cluster (st.shared::cluster via map_shared_rank) ->
+//   one cluster barrier (arrive.release / wait.acquire) ->
+//   every warp picks the same winner from local shared memory and updates from registers.
+// One __syncthreads and one cluster barrier per column; no global-memory round trips.
+// Pivot rule = blas::iamax (src/blas/iamax.rs:6-21): first maximum of |x| by logical row,
+// NaN never wins; multipliers by reciprocal-multiply (src/lapack/getrf.rs:76-81).
+#include <climits>
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "pivot_key.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lair {
+namespace {
+
+constexpr int CL_TPB = 512;
+constexpr int CL_MAXC = 16;
+
+template <class T, int W>
+__global__ void __launch_bounds__(CL_TPB, 1)
+panel_cluster_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __restrict__ ipiv, int row_base,
+                     int32_t* __restrict__ info, int step_base) {
+    using K = PivotKey<T>;
+    using KT = typename K::type;
+    constexpr int NW = CL_TPB / 32;
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) V16 { T v[VEC]; };
+    static_assert(CL_MAXC <= NW, "one pushing warp per peer");
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+
+    __shared__ KT s_wkey[NW];
+    __shared__ int s_wpos[NW];
+    __shared__ __align__(16) T s_wrow[NW][W];
+    __shared__ __align__(16) T s_rows[2][CL_MAXC][W];                   // candidate rows pushed by every CTA
+    __shared__ __align__(16) unsigned long long s_cand[2][CL_MAXC][4];  // {key, pos, recip bits, -}
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    T a[W];
+    const int row = rank * CL_TPB + tid;
+    int pos = row < M ? row : -1;
+    const bool vec_ok = (w == W) && ((lda % VEC) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    if (row < M) {
+        const T* p = A + (long long)row * lda;
+        if (vec_ok) {
+#pragma unroll
+            for (int c = 0; c < W / VEC; ++c) {
+                V16 v = *reinterpret_cast<const V16*>(p + c * VEC);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) a[c * VEC + e] = v.v[e];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < W; ++c) a[c] = (c < w) ? p[c] : T(0);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < W; ++c) a[c] = T(0);
+    }
+    cluster.sync();  // every CTA of the cluster is running before the first remote store
+
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        if (j >= w) break;
+        const int parity = j & 1;
+
+        // (1) warp candidate
+        const bool live = pos >= j;
+        const KT key = live ? K::of(a[j]) : (KT)0;
+        const KT wmax = K::warp_max(key);
+        const bool cand = live && (key == wmax);
+        const unsigned wpos = __reduce_min_sync(kFullMask, cand ? (unsigned)pos : (unsigned)INT_MAX);
+        if (cand && (unsigned)pos == wpos) {
+#pragma unroll
+            for (int c = 0; c < W / VEC; ++c) {
+                V16 v;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v.v[e] = a[c * VEC + e];
+                *reinterpret_cast<V16*>(&s_wrow[warp][c * VEC]) = v;
+            }
+        }
+        if (lane == 0) {
+            s_wkey[warp] = wmax;
+            s_wpos[warp] = (int)wpos;
+        }
+        __syncthreads();
+
+        // (2) every warp derives the CTA candidate; warp p pushes it to CTA p of the cluster
+        {
+            const KT k16 = lane < NW ? s_wkey[lane] : (KT)0;
+            const unsigned p16 = lane < NW ? (unsigned)s_wpos[lane] : 0xffffffffu;
+            const KT cmax = K::warp_max(k16);
+            const bool c16 = (lane < NW) && (k16 == cmax);
+            const unsigned cpos = __reduce_min_sync(kFullMask, c16 ? p16 : 0xffffffffu);
+            const int bw = __ffs(__ballot_sync(kFullMask, c16 && p16 == cpos)) - 1;
+            if (warp < C) {
+                T* dst = cluster.map_shared_rank(&s_rows[parity][rank][0], warp);
+                for (int c = lane; c < W; c += 32) dst[c] = s_wrow[bw][c];
+                if (lane == 0) {
+                    unsigned long long* dc = cluster.map_shared_rank(&s_cand[parity][rank][0], warp);
+                    const T pv = s_wrow[bw][j];
+                    const T rc = (cmax == 0) ? T(0) : T(1) / pv;  // A::one() / pivot (getrf.rs:76)
+                    unsigned long long rbits;
+                    if (sizeof(T) == 8) rbits = (unsigned long long)__double_as_longlong((double)rc);
+                    else rbits = (unsigned long long)__float_as_uint((float)rc);
+                    dc[0] = (unsigned long long)cmax;
+                    dc[1] = (unsigned long long)cpos;
+                    dc[2] = rbits;
+                }
+            }
+        }
+        cluster.sync();
+
+        // (3) every warp picks the same winner from its own shared memory
+        const KT gk = lane < C ? (KT)s_cand[parity][lane][0] : (KT)0;
+        const unsigned gp = lane < C ? (unsigned)s_cand[parity][lane][1] : 0xffffffffu;
+        const KT gmax = K::warp_max(gk);
+        const bool c2 = (lane < C) && (gk == gmax);
+        const unsigned gpos_u = __reduce_min_sync(kFullMask, c2 ? gp : 0xffffffffu);
+        const int gw = __ffs(__ballot_sync(kFullMask, c2 && gp == gpos_u)) - 1;
+        const int gpos = (int)gpos_u;
+        const bool sing = (gmax == 0);
+        if (rank == 0 && tid == 0) {
+            ipiv[j] = row_base + gpos;
+            if (sing) *info = step_base + j;  // last zero-pivot step wins (getrf.rs:72-73)
+        }
+        {
+            const bool was_j = (pos == j), was_w = (pos == gpos);
+            if (was_j) pos = gpos;
+            if (was_w) pos = j;
+        }
+        if (!sing) {
+            const unsigned long long rbits = s_cand[parity][gw][2];
+            T recip;
+            if (sizeof(T) == 8) recip = (T)__longlong_as_double((long long)rbits);
+            else recip = (T)__uint_as_float((unsigned)rbits);
+            if (pos > j) {
+                const T l = a[j] * recip;
+                a[j] = l;
+#pragma unroll
+                for (int c = (j + 1) / VEC; c < W / VEC; ++c) {
+                    V16 v = *reinterpret_cast<const V16*>(&s_rows[parity][gw][c * VEC]);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const int k = c * VEC + e;
+                        if (k > j) a[k] -= l * v.v[e];
+                    }
+                }
+            }
+        }
+    }
+
+    if (pos >= 0) {
+        T* p = A + (long long)pos * lda;
+        if (vec_ok) {
+#pragma unroll
+            for (int c = 0; c < W / VEC; ++c) {
+                V16 v;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v.v[e] = a[c * VEC + e];
+                *reinterpret_cast<V16*>(p + c * VEC) = v;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < W; ++c)
+                if (c < w) p[c] = a[c];
+        }
+    }
+    cluster.sync();  // no CTA leaves while a peer could still address its shared memory
+}
+
+template <class T, int W>
+int launch_cluster(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info,
+                   int32_t step_base, cudaStream_t s) {
+    auto kern = panel_cluster_kernel<T, W>;
+    static int max_cluster = -1;  // largest cluster size this device accepts for the kernel
+    if (max_cluster < 0) {
+        max_cluster = 8;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(16);
+            cfg.blockDim = dim3(CL_TPB);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 16;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters >= 1) max_cluster = 16;
+        }
+        (void)cudaGetLastError();
+    }
+    int need = (int)((rows + CL_TPB - 1) / CL_TPB);
+    int csize = 1;
+    while (csize < need) csize *= 2;
+    if (csize > max_cluster) return LAIR_B200_ERR_UNSUPPORTED;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize);
+    cfg.blockDim = dim3(CL_TPB);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ProfScope prof(kProfPanel, s, 2.0 * (double)rows * (double)w * sizeof(T));
+    LAIR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, d_a, (long long)lda, (int)rows, (int)w, d_ipiv, (int)row_base, d_info,
+                                       (int)step_base));
+    LAIR_LAUNCH_CHECK();
+    return LAIR_B200_OK;
+}
+
+}  // namespace
+
+// Returns LAIR_B200_ERR_UNSUPPORTED (without setting an error) when the panel does not fit one cluster.
+template <class T>
+int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info,
+                      int32_t step_base, cudaStream_t s) {
+    if (w > 32 || rows > (int64_t)CL_MAXC * CL_TPB) return LAIR_B200_ERR_UNSUPPORTED;
+    return launch_cluster<T, 32>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+}
+
+int panel_cluster_max_rows() { return CL_MAXC * CL_TPB; }
+
+template int panel_cluster_dev<float>(int64_t, int64_t, float*, int64_t, int32_t*, int32_t, int32_t*, int32_t, cudaStream_t);
+template int panel_cluster_dev<double>(int64_t, int64_t, double*, int64_t, int32_t*, int32_t, int32_t*, int32_t, cudaStream_t);
+
+}  // namespace lair

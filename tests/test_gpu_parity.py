@@ -234,6 +234,26 @@ def test_blocked_f64_matches_oracle(lair, shape):
     assert be <= 10 * max(be_o, 0.01), (be, be_o)
 
 
+@pytest.mark.parametrize("option,values", [("panel_cluster", (0, 1)), ("gemm_cfg", (1, 2, 3, 0)), ("nb", (64, 128, 512, 256))])
+def test_blocked_f64_kernel_variants(lair, option, values):
+    """Every kernel variant behind a tuning option produces the oracle's pivots and L\\U."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(4242)
+    a0 = _rand(rng, (1100, 900), np.float64)
+    ref = a0.copy()
+    piv_o, sing_o = oracle.getrf(ref)
+    default = _ffi.get_option(option)
+    try:
+        for v in values:
+            _ffi.set_option(option, v)
+            a = a0.copy()
+            piv, sing = lair.lapack.getrf(a)
+            assert piv == piv_o and sing == sing_o, (option, v, _first_divergence(piv, piv_o))
+            assert np.max(np.abs(a - ref)) <= 1e-9 * np.max(np.abs(ref)), (option, v)
+    finally:
+        _ffi.set_option(option, default)
+
+
 @pytest.mark.parametrize("shape", [(300, 300), (1000, 1000), (2000, 300), (300, 900)])
 def test_blocked_f32_matches_oracle(lair, shape):
     rng = np.random.default_rng(shape[0] + 13 * shape[1])

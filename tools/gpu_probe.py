@@ -95,13 +95,28 @@ def sec_ceil():
 def sec_gemm():
     for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
         fn = getattr(L, f"lair_b200_{pfx}gemm_minus_dev")
-        for (m, n, k) in ((8192, 8192, 256), (8192, 8192, 128), (8192, 8192, 32), (4096, 4096, 256), (2048, 2048, 256),
-                          (8192, 128, 128), (8192, 64, 64), (8192, 32, 32), (8192, 64, 256)):
+        for (m, n, k) in ((8192, 8192, 256), (8192, 8192, 512), (8192, 8192, 128), (4096, 4096, 256), (2048, 2048, 256),
+                          (8192, 128, 128), (8192, 64, 64), (8192, 32, 32), (8192, 64, 256), (4096, 64, 128)):
             a = torch.rand(m, k, dtype=dt, device="cuda")
             b = torch.rand(k, n, dtype=dt, device="cuda")
             c = torch.rand(m, n, dtype=dt, device="cuda")
-            best, med = timeit(lambda: _ffi.check(fn(m, n, k, a.data_ptr(), k, b.data_ptr(), n, c.data_ptr(), n, stream())), reps=5)
-            out(bench=f"{pfx}gemm_minus", m=m, n=n, k=k, ms_best=best, ms_med=med, tflops_best=2 * m * n * k / best * 1e-9)
+            for cfg in ((0, 1, 2, 3) if pfx == "d" else (0,)):
+                _ffi.set_option("gemm_cfg", cfg)
+                best, med = timeit(lambda: _ffi.check(fn(m, n, k, a.data_ptr(), k, b.data_ptr(), n, c.data_ptr(), n, stream())), reps=5)
+                out(bench=f"{pfx}gemm_minus", cfg=cfg, m=m, n=n, k=k, ms_best=best, ms_med=med, tflops_best=2 * m * n * k / best * 1e-9)
+            _ffi.set_option("gemm_cfg", 0)
+
+
+def sec_gemmbig():
+    """Only the big trailing-update shape (for an ncu capture of the dominant kernel)."""
+    fn = L.lair_b200_dgemm_minus_dev
+    m = n = 8192
+    k = 256
+    a = torch.rand(m, k, dtype=torch.float64, device="cuda")
+    b = torch.rand(k, n, dtype=torch.float64, device="cuda")
+    c = torch.rand(m, n, dtype=torch.float64, device="cuda")
+    best, med = timeit(lambda: _ffi.check(fn(m, n, k, a.data_ptr(), k, b.data_ptr(), n, c.data_ptr(), n, stream())), reps=3, warm=1)
+    out(bench="dgemm_minus_big", m=m, n=n, k=k, ms_best=best, tflops_best=2 * m * n * k / best * 1e-9)
 
 
 def sec_batched():
@@ -130,9 +145,12 @@ def sec_panel():
             a = a0.clone()
             ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
             info = torch.empty(1, dtype=torch.int32, device="cuda")
-            best, med = timeit(lambda: _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
-                               setup=lambda: a.copy_(a0))
-            out(bench=f"{pfx}panel", m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
+            for cl in (1, 0):
+                _ffi.set_option("panel_cluster", cl)
+                best, med = timeit(lambda: _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
+                                   setup=lambda: a.copy_(a0))
+                out(bench=f"{pfx}panel", cluster=cl, m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
+            _ffi.set_option("panel_cluster", 1)
 
 
 def sec_getrf():
