@@ -135,6 +135,7 @@ struct Options {
     int64_t lookahead = 1;   // overlap panel k+1 with trailing update k
     int64_t batched_cfg = 0; // occupancy variant of the batched kernel (batched_lu.cu)
     int64_t panel_cluster = 1;  // use the single-cluster DSMEM panel kernel when the panel fits
+    int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
 };
 

@@ -173,6 +173,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.panel_cluster = value;
     } else if (!strcmp(name, "gemm_cfg")) {
         o.gemm_cfg = value;
+    } else if (!strcmp(name, "panel_group")) {
+        o.panel_group = value;
     } else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;
@@ -189,6 +191,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "batched_cfg")) *value = o.batched_cfg;
     else if (!strcmp(name, "panel_cluster")) *value = o.panel_cluster;
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
+    else if (!strcmp(name, "panel_group")) *value = o.panel_group;
     else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;

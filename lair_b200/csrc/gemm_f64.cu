@@ -89,6 +89,36 @@ __device__ __forceinline__ void load_stage(double* __restrict__ sa, double* __re
     }
 }
 
+// Interior tiles with 16-byte-aligned operands: per-thread source pointers are fixed at kernel
+// start and only advance by BK (A) / BK rows (B) per k-tile -- no bounds logic in the loop.
+template <class C>
+__device__ __forceinline__ void load_stage_fast(double* __restrict__ sa, double* __restrict__ sb, const double* __restrict__ a_src,
+                                                long long lda, const double* __restrict__ b_src, long long ldb, int tid) {
+    constexpr int A_CPR = BK / 2, A_ITERS = C::BM * A_CPR / C::THREADS, A_ROWS_PER_ITER = C::THREADS / A_CPR;
+    static_assert(C::BM * A_CPR % C::THREADS == 0 && C::THREADS % A_CPR == 0, "A tile must divide evenly");
+    double* da = sa + (tid / A_CPR) * C::LDA_S + (tid % A_CPR) * 2;
+#pragma unroll
+    for (int i = 0; i < A_ITERS; ++i)
+        cp_async16_zfill(da + i * A_ROWS_PER_ITER * C::LDA_S, a_src + (long long)(i * A_ROWS_PER_ITER) * lda, 16);
+    constexpr int B_CPR = C::BN / 2;
+    if constexpr (C::THREADS % B_CPR == 0) {
+        constexpr int B_ITERS = BK * B_CPR / C::THREADS, B_ROWS_PER_ITER = C::THREADS / B_CPR;
+        static_assert(BK * B_CPR % C::THREADS == 0, "B tile must divide evenly");
+        double* db = sb + (tid / B_CPR) * C::LDB_S + (tid % B_CPR) * 2;
+#pragma unroll
+        for (int i = 0; i < B_ITERS; ++i)
+            cp_async16_zfill(db + i * B_ROWS_PER_ITER * C::LDB_S, b_src + (long long)(i * B_ROWS_PER_ITER) * ldb, 16);
+    } else {
+        // fewer threads than chunks per row: each thread walks columns within a row
+        constexpr int B_CHUNKS = BK * B_CPR;
+#pragma unroll
+        for (int c = tid; c < B_CHUNKS; c += C::THREADS) {
+            const int r = c / B_CPR, nc = (c % B_CPR) * 2;
+            cp_async16_zfill(sb + r * C::LDB_S + nc, b_src + (long long)r * ldb + nc, 16);
+        }
+    }
+}
+
 template <class C, int WARPS_M, int WARPS_N, int WTM, int WTN, int MINB, bool ALIGNED>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
@@ -103,38 +133,64 @@ dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __
     const int m0 = (tile % tiles_m) * C::BM, n0 = (tile / tiles_m) * C::BN;
     const int KT = (K + BK - 1) / BK;
 
+    // interior tile with aligned operands: fixed per-thread source pointers, no bounds logic
+    const bool fast = ALIGNED && (m0 + C::BM <= M) && (n0 + C::BN <= N) && (K % BK == 0);
+    constexpr int A_CPR = BK / 2, B_CPR = C::BN / 2;
+    const double* a_thr = A + (long long)(m0 + tid / A_CPR) * lda + (tid % A_CPR) * 2;
+    const double* b_thr = (C::THREADS % B_CPR == 0) ? B + (long long)(tid / B_CPR) * ldb + n0 + (tid % B_CPR) * 2 : B + n0;
+    auto issue_stage = [&](int kt_load) {
+        const int slot = kt_load % C::STAGES;
+        double* sa_ = smem + slot * C::STAGE_ELEMS;
+        double* sb_ = sa_ + C::A_ELEMS;
+        if (fast)
+            load_stage_fast<C>(sa_, sb_, a_thr + (long long)kt_load * BK, lda, b_thr + (long long)kt_load * BK * ldb, ldb, tid);
+        else
+            load_stage<C, ALIGNED>(sa_, sb_, A, lda, B, ldb, M, N, K, m0, n0, kt_load * BK, tid);
+    };
+
     // operand pipeline first, so the C loads below overlap it
 #pragma unroll
     for (int s = 0; s < C::STAGES - 1; ++s) {
-        if (s < KT)
-            load_stage<C, ALIGNED>(smem + s * C::STAGE_ELEMS, smem + s * C::STAGE_ELEMS + C::A_ELEMS, A, lda, B, ldb, M, N, K, m0, n0,
-                                   s * BK, tid);
+        if (s < KT) issue_stage(s);
         cp_async_commit();
     }
 
     // accumulators start at -C: each thread owns (row g, cols 2t, 2t+1) of every 8x8 tile
     double acc[WTM][WTN][2];
     const bool vec_ok = ALIGNED && ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cm) & 15) == 0);
+    // interior tiles (the common case) take a branch-free path so all C loads are in flight at
+    // once; a conditional per element would serialise one DRAM latency per load
+    const bool interior = vec_ok && (m0 + C::BM <= M) && (n0 + C::BN <= N);
+    if (interior) {
+        const double* cbase = Cm + (long long)(m0 + wm * WTM * 8 + g) * ldc + n0 + wn * WTN * 8 + 2 * t;
+        double2 cv[WTM][WTN];
 #pragma unroll
-    for (int i = 0; i < WTM; ++i) {
-        const int row = m0 + (wm * WTM + i) * 8 + g;
+        for (int i = 0; i < WTM; ++i)
 #pragma unroll
-        for (int j = 0; j < WTN; ++j) {
-            const int col = n0 + (wn * WTN + j) * 8 + 2 * t;
-            double c0 = 0.0, c1 = 0.0;
-            if (row < M) {
-                const double* p = Cm + (long long)row * ldc + col;
-                if (vec_ok && col + 1 < N) {
-                    const double2 v = *reinterpret_cast<const double2*>(p);
-                    c0 = v.x;
-                    c1 = v.y;
-                } else {
+            for (int j = 0; j < WTN; ++j) cv[i][j] = *reinterpret_cast<const double2*>(cbase + (long long)(i * 8) * ldc + j * 8);
+#pragma unroll
+        for (int i = 0; i < WTM; ++i)
+#pragma unroll
+            for (int j = 0; j < WTN; ++j) {
+                acc[i][j][0] = -cv[i][j].x;
+                acc[i][j][1] = -cv[i][j].y;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < WTM; ++i) {
+            const int row = m0 + (wm * WTM + i) * 8 + g;
+#pragma unroll
+            for (int j = 0; j < WTN; ++j) {
+                const int col = n0 + (wn * WTN + j) * 8 + 2 * t;
+                double c0 = 0.0, c1 = 0.0;
+                if (row < M) {
+                    const double* p = Cm + (long long)row * ldc + col;
                     if (col < N) c0 = p[0];
                     if (col + 1 < N) c1 = p[1];
                 }
+                acc[i][j][0] = -c0;
+                acc[i][j][1] = -c1;
             }
-            acc[i][j][0] = -c0;
-            acc[i][j][1] = -c1;
         }
     }
 
@@ -143,11 +199,7 @@ dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __
         __syncthreads();
         {
             const int nk = kt + C::STAGES - 1;
-            if (nk < KT) {
-                const int slot = nk % C::STAGES;
-                load_stage<C, ALIGNED>(smem + slot * C::STAGE_ELEMS, smem + slot * C::STAGE_ELEMS + C::A_ELEMS, A, lda, B, ldb, M, N, K,
-                                       m0, n0, nk * BK, tid);
-            }
+            if (nk < KT) issue_stage(nk);
             cp_async_commit();
         }
         const double* sa = smem + (kt % C::STAGES) * C::STAGE_ELEMS;
@@ -168,6 +220,15 @@ dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __
     cp_async_wait<0>();
 
     // epilogue: C = -(acc)
+    if (interior) {
+        double* cbase = Cm + (long long)(m0 + wm * WTM * 8 + g) * ldc + n0 + wn * WTN * 8 + 2 * t;
+#pragma unroll
+        for (int i = 0; i < WTM; ++i)
+#pragma unroll
+            for (int j = 0; j < WTN; ++j)
+                *reinterpret_cast<double2*>(cbase + (long long)(i * 8) * ldc + j * 8) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < WTM; ++i) {
         const int row = m0 + (wm * WTM + i) * 8 + g;

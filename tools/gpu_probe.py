@@ -145,12 +145,14 @@ def sec_panel():
             a = a0.clone()
             ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
             info = torch.empty(1, dtype=torch.int32, device="cuda")
-            for cl in (1, 0):
+            for cl, grp in ((1, 1), (1, 2), (1, 4), (1, 8), (0, 4)):
                 _ffi.set_option("panel_cluster", cl)
+                _ffi.set_option("panel_group", grp)
                 best, med = timeit(lambda: _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
                                    setup=lambda: a.copy_(a0))
-                out(bench=f"{pfx}panel", cluster=cl, m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
+                out(bench=f"{pfx}panel", cluster=cl, group=grp, m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
             _ffi.set_option("panel_cluster", 1)
+            _ffi.set_option("panel_group", 4)
 
 
 def sec_getrf():
