@@ -140,6 +140,10 @@ LAIR_B200_API int64_t lair_b200_launch_count(void);
 LAIR_B200_API int lair_b200_profile_begin(void);
 LAIR_B200_API int lair_b200_profile_end(void);
 LAIR_B200_API int lair_b200_profile_get(const char* family, double* ms, int64_t* launches, double* work);
+/* Debug aid: with option "panel_timing" = 1 the cluster panel kernel accumulates SM-cycle counts
+ * of its per-column phases; out8 = {candidate, block barrier, push, cluster barrier, winner,
+ * update, columns, 0}. */
+LAIR_B200_API int lair_b200_debug_panel_timing(long long* out8, int clear);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "lair_b200_set_option": [ctypes.c_char_p, i64],
     "lair_b200_get_option": [ctypes.c_char_p, ctypes.POINTER(i64)],
     "lair_b200_launch_count": [],
+    "lair_b200_debug_panel_timing": [ctypes.POINTER(ctypes.c_longlong), cint],
     "lair_b200_profile_begin": [],
     "lair_b200_profile_end": [],
     "lair_b200_profile_get": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),

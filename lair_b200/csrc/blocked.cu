@@ -89,6 +89,13 @@ int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const
     LAIR_REQUIRE(n >= 0 && nrhs >= 0 && lda >= n && ldb >= nrhs, "getrs: bad shape");
     if (n == 0 || nrhs == 0) return LAIR_B200_OK;
     LAIR_CHECK(laswp_dev<T>(nrhs, d_b, ldb, 0, n, d_ipiv, s));
+    if constexpr (sizeof(T) == 8) {
+        if (ctx().opt.trsm_dataflow) {
+            // one persistent dataflow kernel per triangle (trsm_dataflow.cu)
+            LAIR_CHECK(dtrsm_dataflow_dev(false, n, nrhs, d_lu, lda, d_b, ldb, s));
+            return dtrsm_dataflow_dev(true, n, nrhs, d_lu, lda, d_b, ldb, s);
+        }
+    }
     LAIR_CHECK(trsm_lower_unit_dev<T>(n, nrhs, d_lu, lda, d_b, ldb, s));
     return trsm_upper_dev<T>(n, nrhs, d_lu, lda, d_b, ldb, s);
 }

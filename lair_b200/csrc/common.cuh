@@ -136,6 +136,8 @@ struct Options {
     int64_t batched_cfg = 0; // occupancy variant of the batched kernel (batched_lu.cu)
     int64_t panel_cluster = 1;  // use the single-cluster DSMEM panel kernel when the panel fits
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
+    int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
+    int64_t trsm_dataflow = 1;  // f64 getrs: persistent dataflow triangular solves (trsm_dataflow.cu)
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
 };
 
@@ -180,6 +182,9 @@ template <class T> int panel_max_width(int64_t rows);
 // single-cluster DSMEM variant (panel_cluster.cu); LAIR_B200_ERR_UNSUPPORTED when it does not fit
 template <class T> int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 int panel_cluster_max_rows();
+int panel_cluster_timing(long long* out8, bool clear);
+// X = T^-1 B in place, T = unit-lower / upper triangle of d_lu (trsm_dataflow.cu)
+int dtrsm_dataflow_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);
 // 1 if a panel exchange timed out since the last clear (results are then invalid)
 int panel_error_flag(bool clear);
 

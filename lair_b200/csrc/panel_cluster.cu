@@ -36,6 +36,19 @@ namespace {
 constexpr int CL_TPB = 512;
 constexpr int CL_MAXC = 16;
 
+// Debug aid: cycle stamps of the per-column phases (rank 0, thread 0), summed over columns.
+// [0] candidate+park, [1] __syncthreads, [2] CTA candidate + push, [3] cluster barrier,
+// [4] winner select, [5] update, [6] columns timed.  Enabled by option "panel_timing".
+__device__ long long g_cl_timing[8];
+#define CL_STAMP(slot)                                        \
+    do {                                                      \
+        if (timing && rank == 0 && tid == 0) {                \
+            const long long now_ = clock64();                 \
+            g_cl_timing[slot] += now_ - tprev;                \
+            tprev = now_;                                     \
+        }                                                     \
+    } while (0)
+
 template <class T, int W>
 struct ClusterSmem {
     static constexpr int NW = CL_TPB / 32;
@@ -51,10 +64,11 @@ struct ClusterSmem {
 template <class T, int W, int GS>
 __global__ void __launch_bounds__(CL_TPB, 1)
 panel_cluster_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __restrict__ ipiv, int row_base,
-                     int32_t* __restrict__ info, int step_base) {
+                     int32_t* __restrict__ info, int step_base, int timing) {
     using K = PivotKey<T>;
     using KT = typename K::type;
     using SM = ClusterSmem<T, W>;
+    long long tprev = 0;
     constexpr int NW = SM::NW;
     constexpr int VEC = 16 / sizeof(T);
     constexpr int OUT_LD = SM::OUT_LD;
@@ -108,6 +122,7 @@ panel_cluster_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
             const int j = jb + c;
             if (j >= w) break;  // uniform
             const int parity = j & 1;
+            if (timing && rank == 0 && tid == 0) tprev = clock64();
             T* rows_p = s_rows + parity * (CL_MAXC * W);
             unsigned long long* cand_p = s_cand + parity * (CL_MAXC * 4);
 
@@ -130,7 +145,9 @@ panel_cluster_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 s_wkey[warp] = wmax;
                 s_wpos[warp] = (int)wpos;
             }
+            CL_STAMP(0);
             __syncthreads();
+            CL_STAMP(1);
 
             // (2) every warp derives the CTA candidate; warp p pushes it to CTA p of the cluster
             {
@@ -156,7 +173,9 @@ panel_cluster_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                     }
                 }
             }
+            CL_STAMP(2);
             cluster.sync();
+            CL_STAMP(3);
 
             // (3) every warp picks the same winner from its own shared memory
             const KT gk = lane < C ? (KT)cand_p[lane * 4 + 0] : (KT)0;
@@ -171,6 +190,7 @@ panel_cluster_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 ipiv[j] = row_base + gpos;
                 if (sing) *info = step_base + j;  // last zero-pivot step wins (getrf.rs:72-73)
             }
+            CL_STAMP(4);
             const bool was_j = (pos == j), was_w = (pos == gpos);
             if (was_j) pos = gpos;
             if (was_w) {
@@ -203,6 +223,8 @@ panel_cluster_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 }
                 my_out[j] = a[c];  // multiplier (or the untouched entry of a singular step)
             }
+            CL_STAMP(5);
+            if (timing && rank == 0 && tid == 0) g_cl_timing[6] += 1;
         }
         // rotate the window: column jb+GS moves to index 0
 #pragma unroll
@@ -273,7 +295,7 @@ int launch_cluster(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv
     cfg.numAttrs = 1;
     ProfScope prof(kProfPanel, s, 2.0 * (double)rows * (double)w * sizeof(T));
     LAIR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, d_a, (long long)lda, (int)rows, (int)w, d_ipiv, (int)row_base, d_info,
-                                       (int)step_base));
+                                       (int)step_base, (int)ctx().opt.panel_timing));
     LAIR_LAUNCH_CHECK();
     return LAIR_B200_OK;
 }
@@ -292,6 +314,17 @@ int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_i
 }
 
 int panel_cluster_max_rows() { return CL_MAXC * CL_TPB; }
+
+// Debug: read (and optionally clear) the phase cycle counters of the cluster panel kernel.
+int panel_cluster_timing(long long* out8, bool clear) {
+    LAIR_CUDA_CHECK(cudaDeviceSynchronize());
+    LAIR_CUDA_CHECK(cudaMemcpyFromSymbol(out8, g_cl_timing, 8 * sizeof(long long)));
+    if (clear) {
+        long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        LAIR_CUDA_CHECK(cudaMemcpyToSymbol(g_cl_timing, z, sizeof(z)));
+    }
+    return LAIR_B200_OK;
+}
 
 template int panel_cluster_dev<float>(int64_t, int64_t, float*, int64_t, int32_t*, int32_t, int32_t*, int32_t, cudaStream_t);
 template int panel_cluster_dev<double>(int64_t, int64_t, double*, int64_t, int32_t*, int32_t, int32_t*, int32_t, cudaStream_t);

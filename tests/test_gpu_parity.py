@@ -335,6 +335,26 @@ def test_blocked_getrs_matches_oracle(lair, dt, n, nrhs):
     assert one.shape == (n,) and np.allclose(one, x[:, 0], rtol=0, atol=1e3 * np.finfo(dt).eps * np.max(np.abs(x)))
 
 
+@pytest.mark.parametrize("n,nrhs", [(200, 3), (777, 5), (1000, 64), (1030, 65), (2048, 130)])
+def test_getrs_dataflow_vs_recursive(lair, n, nrhs):
+    """The persistent dataflow triangular solves and the recursive TRSM agree with the oracle."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(n * 3 + nrhs)
+    a0 = _rand(rng, (n, n), np.float64)
+    b = _rand(rng, (n, nrhs), np.float64)
+    lu = a0.copy()
+    piv, _ = oracle.getrf(lu)
+    xo = np.stack([oracle.getrs(lu, piv, np.ascontiguousarray(b[:, r])) for r in range(0, nrhs, max(1, nrhs // 3))], axis=1)
+    try:
+        for df in (1, 0):
+            _ffi.set_option("trsm_dataflow", df)
+            x = lair.lapack.getrs(lu, piv, b)
+            got = x[:, ::max(1, nrhs // 3)]
+            assert np.max(np.abs(got - xo)) <= 1e-7 * np.max(np.abs(xo)), (df, np.max(np.abs(got - xo)))
+    finally:
+        _ffi.set_option("trsm_dataflow", 1)
+
+
 def test_equation_solve_end_to_end(lair):
     rng = np.random.default_rng(2)
     n = 1500

@@ -155,6 +155,32 @@ def sec_panel():
             _ffi.set_option("panel_group", 4)
 
 
+def sec_paneltiming():
+    """Per-phase SM-cycle breakdown of the cluster panel kernel (debug counters)."""
+    buf = (ctypes.c_longlong * 8)()
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for m in (1024, 8192):
+            w = 32
+            a0 = torch.rand(m, w, dtype=dt, device="cuda")
+            a = a0.clone()
+            ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
+            info = torch.empty(1, dtype=torch.int32, device="cuda")
+            _ffi.set_option("panel_timing", 1)
+            _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream()))
+            torch.cuda.synchronize()
+            _ffi.check(L.lair_b200_debug_panel_timing(buf, 1))
+            for _ in range(3):
+                a.copy_(a0)
+                _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream()))
+            torch.cuda.synchronize()
+            _ffi.check(L.lair_b200_debug_panel_timing(buf, 1))
+            _ffi.set_option("panel_timing", 0)
+            cols = max(1, buf[6])
+            names = ["candidate", "syncthreads", "cta_cand_push", "cluster_sync", "winner", "update"]
+            out(bench=f"{pfx}panel_phases", m=m, columns=int(buf[6]), cycles_per_column={n: buf[i] / cols for i, n in enumerate(names)})
+
+
 def sec_getrf():
     for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
         fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
@@ -194,15 +220,20 @@ def sec_getrs():
         ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
         info = torch.empty(1, dtype=torch.int32, device="cuda")
         _ffi.check(getattr(L, f"lair_b200_{pfx}getrf_dev")(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream()))
-        b0 = torch.rand(n, nrhs, dtype=dt, device="cuda")
-        b = b0.clone()
         fn = getattr(L, f"lair_b200_{pfx}getrs_dev")
-        l0 = _ffi.launch_count()
-        best, med = timeit(lambda: _ffi.check(fn(n, nrhs, a.data_ptr(), n, ipiv.data_ptr(), b.data_ptr(), nrhs, stream())), reps=3, warm=1,
-                           setup=lambda: b.copy_(b0))
-        launches = (_ffi.launch_count() - l0) // 4
-        res = float(torch.linalg.norm(a0 @ b - b0) / (torch.linalg.norm(a0) * torch.linalg.norm(b) * n * 2.0 ** -53))
-        out(bench=f"{pfx}getrs", n=n, nrhs=nrhs, ms_best=best, launches=launches, tflops=2 * n * n * nrhs / best * 1e-9, residual=res)
+        for nrhs_ in (64, 1, 256):
+            b0 = torch.rand(n, nrhs_, dtype=dt, device="cuda")
+            b = b0.clone()
+            for df in (1, 0):
+                _ffi.set_option("trsm_dataflow", df)
+                l0 = _ffi.launch_count()
+                best, med = timeit(lambda: _ffi.check(fn(n, nrhs_, a.data_ptr(), n, ipiv.data_ptr(), b.data_ptr(), nrhs_, stream())),
+                                   reps=3, warm=1, setup=lambda: b.copy_(b0))
+                launches = (_ffi.launch_count() - l0) // 4
+                res = float(torch.linalg.norm(a0 @ b - b0) / (torch.linalg.norm(a0) * torch.linalg.norm(b) * n * 2.0 ** -53))
+                out(bench=f"{pfx}getrs", dataflow=df, n=n, nrhs=nrhs_, ms_best=best, launches=launches,
+                    tflops=2 * n * n * nrhs_ / best * 1e-9, residual=res)
+            _ffi.set_option("trsm_dataflow", 1)
 
 
 if __name__ == "__main__":
