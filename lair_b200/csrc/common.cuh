@@ -134,7 +134,8 @@ struct Options {
     int64_t small_n = 128;   // max(m, n) handled by the single-CTA exact kernel
     int64_t lookahead = 1;   // overlap panel k+1 with trailing update k
     int64_t batched_cfg = 0; // occupancy variant of the batched kernel (batched_lu.cu)
-    int64_t panel_cluster = 1;  // use the single-cluster DSMEM panel kernel when the panel fits
+    int64_t panel_cluster = 2;  // panels that fit one cluster: 2 blocked DSMEM kernel, 1 row-per-thread DSMEM kernel, 0 global-memory exchange
+    int64_t panel_rpt = 4;      // rows per thread of the blocked cluster panel kernel (2, 4, 8)
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
     int64_t trsm_dataflow = 1;  // f64 getrs: persistent dataflow triangular solves (trsm_dataflow.cu)
@@ -183,6 +184,9 @@ template <class T> int panel_max_width(int64_t rows);
 template <class T> int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 int panel_cluster_max_rows();
 int panel_cluster_timing(long long* out8, bool clear);
+// in-kernel blocked cluster panel (panel_blocked.cu): 8-column register sub-panels, RPT rows per thread
+template <class T> int panel_blocked_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
+int panel_blocked_timing(long long* out8, bool clear);
 // X = T^-1 B in place, T = unit-lower / upper triangle of d_lu (trsm_dataflow.cu)
 int dtrsm_dataflow_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);
 // 1 if a panel exchange timed out since the last clear (results are then invalid)

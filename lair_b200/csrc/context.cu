@@ -175,6 +175,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.gemm_cfg = value;
     } else if (!strcmp(name, "panel_group")) {
         o.panel_group = value;
+    } else if (!strcmp(name, "panel_rpt")) {
+        o.panel_rpt = value;
     } else if (!strcmp(name, "panel_timing")) {
         o.panel_timing = value;
     } else if (!strcmp(name, "trsm_dataflow")) {
@@ -196,6 +198,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "panel_cluster")) *value = o.panel_cluster;
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
     else if (!strcmp(name, "panel_group")) *value = o.panel_group;
+    else if (!strcmp(name, "panel_rpt")) *value = o.panel_rpt;
     else if (!strcmp(name, "panel_timing")) *value = o.panel_timing;
     else if (!strcmp(name, "trsm_dataflow")) *value = o.trsm_dataflow;
     else {
@@ -207,6 +210,9 @@ int lair_b200_get_option(const char* name, int64_t* value) {
 
 int64_t lair_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int lair_b200_debug_panel_timing(long long* out8, int clear) { return panel_cluster_timing(out8, clear != 0); }
+int lair_b200_debug_panel_timing(long long* out8, int clear) {
+    if (g_ctx.opt.panel_cluster >= 2) return panel_blocked_timing(out8, clear != 0);
+    return panel_cluster_timing(out8, clear != 0);
+}
 
 }  // extern "C"

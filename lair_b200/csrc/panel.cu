@@ -343,7 +343,9 @@ int panel_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int
     using PT = PanelTable<T>;
     LAIR_REQUIRE(rows >= 1 && w >= 1 && w <= rows, "panel: bad shape rows=%lld w=%lld", (long long)rows, (long long)w);
     if (ctx().opt.panel_cluster && rows <= panel_cluster_max_rows() && w <= 32) {
-        int st = panel_cluster_dev<T>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+        // 2 (default): in-kernel blocked cluster kernel; 1: one-row-per-thread cluster kernel
+        int st = (ctx().opt.panel_cluster >= 2) ? panel_blocked_dev<T>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)
+                                                : panel_cluster_dev<T>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
         if (st != LAIR_B200_ERR_UNSUPPORTED) return st;
     }
     if (w <= PT::W0 && rows <= PT::V0::capacity_rows(nullptr))

@@ -145,14 +145,16 @@ def sec_panel():
             a = a0.clone()
             ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
             info = torch.empty(1, dtype=torch.int32, device="cuda")
-            for cl, grp in ((1, 1), (1, 2), (1, 4), (1, 8), (0, 4)):
+            for cl, grp, rpt in ((2, 4, 2), (2, 4, 4), (2, 4, 8), (1, 4, 4), (0, 4, 4)):
                 _ffi.set_option("panel_cluster", cl)
                 _ffi.set_option("panel_group", grp)
+                _ffi.set_option("panel_rpt", rpt)
                 best, med = timeit(lambda: _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
                                    setup=lambda: a.copy_(a0))
-                out(bench=f"{pfx}panel", cluster=cl, group=grp, m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
-            _ffi.set_option("panel_cluster", 1)
+                out(bench=f"{pfx}panel", cluster=cl, group=grp, rpt=rpt, m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
+            _ffi.set_option("panel_cluster", 2)
             _ffi.set_option("panel_group", 4)
+            _ffi.set_option("panel_rpt", 4)
 
 
 def sec_paneltiming():
@@ -178,7 +180,8 @@ def sec_paneltiming():
             _ffi.set_option("panel_timing", 0)
             cols = max(1, buf[6])
             names = ["candidate", "syncthreads", "cta_cand_push", "cluster_sync", "winner", "update"]
-            out(bench=f"{pfx}panel_phases", m=m, columns=int(buf[6]), cycles_per_column={n: buf[i] / cols for i, n in enumerate(names)})
+            out(bench=f"{pfx}panel_phases", kernel=_ffi.get_option("panel_cluster"), rpt=_ffi.get_option("panel_rpt"), m=m,
+                columns=int(buf[6]), cycles_per_column={n: buf[i] / cols for i, n in enumerate(names)})
 
 
 def sec_getrf():
