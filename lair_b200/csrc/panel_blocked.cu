@@ -110,12 +110,15 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
     __shared__ int s_wrow[NW];  // local row index (0..PB_ROWS) of each warp's candidate
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    long long tprev = 0;
+    // debug phase timing: accumulated in registers, flushed once at the end (a global RMW per
+    // stamp would add an L2 round trip to every phase it tries to measure)
+    long long tprev = 0, tacc0 = 0, tacc1 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, tacc5 = 0, tcols = 0;
+    const long long tstart = clock64();
 #define PB_STAMP(slot)                                  \
     do {                                                \
         if (timing && rank == 0 && tid == 0) {          \
             const long long now_ = clock64();           \
-            g_pb_timing[slot] += now_ - tprev;          \
+            tacc##slot += now_ - tprev;                 \
             tprev = now_;                               \
         }                                               \
     } while (0)
@@ -307,7 +310,7 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 // rows that are (or were) pivots keep a stale window: their entries already sit in the panel
             }
             PB_STAMP(5);
-            if (timing && rank == 0 && tid == 0) g_pb_timing[6] += 1;
+            if (timing && rank == 0 && tid == 0) tcols += 1;
         }
 
         const int c1 = sb + SW;           // first parked column
@@ -379,6 +382,16 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
         }
     }
     cluster.sync();  // no CTA leaves while a peer could still address its shared memory
+    if (timing && rank == 0 && tid == 0) {
+        g_pb_timing[0] += tacc0;
+        g_pb_timing[1] += tacc1;
+        g_pb_timing[2] += tacc2;
+        g_pb_timing[3] += tacc3;
+        g_pb_timing[4] += tacc4;
+        g_pb_timing[5] += tacc5;
+        g_pb_timing[6] += tcols;
+        g_pb_timing[7] += clock64() - tstart;  // whole kernel, thread 0 of rank 0
+    }
 #undef PB_STAMP
 }
 

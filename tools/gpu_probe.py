@@ -181,7 +181,15 @@ def sec_paneltiming():
             cols = max(1, buf[6])
             names = ["candidate", "syncthreads", "cta_cand_push", "cluster_sync", "winner", "update"]
             out(bench=f"{pfx}panel_phases", kernel=_ffi.get_option("panel_cluster"), rpt=_ffi.get_option("panel_rpt"), m=m,
-                columns=int(buf[6]), cycles_per_column={n: buf[i] / cols for i, n in enumerate(names)})
+                columns=int(buf[6]), cycles_per_column={n: buf[i] / cols for i, n in enumerate(names)},
+                kernel_cycles_per_launch=buf[7] / 3)
+            # fixed vs per-column cost: whole-call time for narrower panels
+            for ww in (8, 16, 24, 32):
+                aw0 = torch.rand(m, ww, dtype=dt, device="cuda")
+                aw = aw0.clone()
+                best, med = timeit(lambda: _ffi.check(fn(m, ww, aw.data_ptr(), ww, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
+                                   setup=lambda: aw.copy_(aw0))
+                out(bench=f"{pfx}panel_width", m=m, w=ww, us_total=best * 1e3)
 
 
 def sec_getrf():
