@@ -135,7 +135,7 @@ struct Options {
     int64_t lookahead = 1;   // overlap panel k+1 with trailing update k
     int64_t batched_cfg = 0; // occupancy variant of the batched kernel (batched_lu.cu)
     int64_t panel_cluster = 2;  // panels that fit one cluster: 2 blocked DSMEM kernel, 1 row-per-thread DSMEM kernel, 0 global-memory exchange
-    int64_t panel_rpt = 4;      // rows per thread of the blocked cluster panel kernel (2, 4, 8)
+    int64_t panel_rpt = 2;      // rows per thread of the blocked cluster panel kernel (1, 2, 4)
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
     int64_t trsm_dataflow = 1;  // f64 getrs: persistent dataflow triangular solves (trsm_dataflow.cu)

@@ -1,26 +1,29 @@
 // Panel factorization, third generation: one thread-block cluster, the (rows x 32) panel
 // resident in SHARED memory, factored as four 8-column sub-panels held in REGISTERS.
 //
-// Why: measured on B200 (profiles/r1_panel_phases.md) the per-column cost of the earlier
-// kernels (one row per thread, 16 warps per CTA) was ~4000 cycles, dominated by fixed
-// per-warp work (REDUX arg-max, barriers, serialized shared-memory latency) and only ~3 % by
-// the rank-1 update itself.  This kernel keeps the same exchange (candidate rows pushed
-// through distributed shared memory, one cluster barrier per column) but:
-//   * every thread owns RPT rows, so a CTA of 512 rows needs only 512/RPT threads -- 4x
-//     fewer warps contend for the reduction units and barrier skew shrinks;
-//   * only the active 8-column sub-panel lives in registers (static indices, 8 column steps
-//     compiled once and reused for the four sub-panels -> small instruction footprint);
-//     the other columns stay parked in shared memory and are updated ONCE per sub-panel with
-//     a rank-8 update (8 FMAs per element per smem round trip instead of 1);
-//   * the arg-max uses the top 32 bits of |x| as a coarse key (one REDUX + one vote); the
+// Why (measurements in profiles/r1_panel_phases.md, profiles/r1_latbench_b200.jsonl): the
+// first panel kernels (one row per thread, 16 warps per CTA) spent ~4000 cycles per column,
+// only ~3 % of it in the rank-1 update; every phase was a chain of dependent 20-30-cycle
+// instructions, and a DSMEM *push* exchange costs a warp one remote round trip per peer
+// (1442 cycles for 16 CTAs) while remote *loads* pipeline.  This kernel therefore:
+//   * gives every thread RPT rows, so a CTA of 512 rows is 512/RPT threads -- fewer warps
+//     contend for the reduction units and the block barrier is cheap;
+//   * keeps only the active 8-column sub-panel in registers, as a SLIDING window (a[r][0] is
+//     always the current column; the rank-1 update writes its result one slot down), so the
+//     column step is a rolled loop with a small instruction footprint; the other columns stay
+//     parked in shared memory and are updated ONCE per sub-panel with a rank-8 update;
+//   * exchanges candidates by PULL: each CTA publishes its candidate (key, position, row) in
+//     its own shared memory, ONE cluster barrier, then every warp fetches the records and
+//     rows of its share of the peers with remote loads that are all in flight at once;
+//   * finds arg-max with the top 32 bits of |x| as a coarse key (one REDUX + one vote); the
 //     exact 64-bit comparison runs only among lanes that tie on the coarse key.
-// In-kernel algorithm per sub-panel s (columns 8s..8s+7), exactly the blocked LU recursion
-// of the reference's recursive variant (src/lapack/getrf.rs:216-322) at width 8:
+// In-kernel algorithm per sub-panel s (columns 8s..8s+7) = the blocked LU recursion of the
+// reference's recursive variant (src/lapack/getrf.rs:216-322) at width 8:
 //   8 x { arg-max (src/blas/iamax.rs:6-21) -> exchange -> scale by reciprocal, rank-1 update
-//         of the sub-panel columns in registers },
+//         of the sub-panel columns in registers (src/lapack/getrf.rs:76-87) },
 //   U12 = L11^-1 * (pivot rows' parked columns)        [trsm, redundantly per CTA, tiny]
-//   parked columns of live rows -= L21 * U12           [rank-8 update from registers]
-// Row interchanges stay logical (`pos`), rows are written to their final positions once.
+//   parked columns of live rows -= L21 * U12           [rank-8 update]
+// Row interchanges stay logical (`pos`); rows are written to their final positions once.
 #include <climits>
 #include <cooperative_groups.h>
 
@@ -36,6 +39,7 @@ constexpr int PB_W = 32;       // panel width handled by one launch
 constexpr int PB_SW = 8;       // sub-panel width (register resident)
 constexpr int PB_ROWS = 512;   // rows per CTA
 constexpr int PB_MAXC = 16;    // CTAs per cluster
+constexpr unsigned PB_NOPOS = 0x7fffffffu;
 
 __device__ long long g_pb_timing[8];
 
@@ -44,42 +48,33 @@ struct PBSmem {
     static constexpr int VEC = 16 / sizeof(T);
     static constexpr int LD = PB_W + VEC;  // row pitch: 16-byte aligned rows, conflict-free 128-bit row access
     static constexpr size_t panel_bytes = (size_t)PB_ROWS * LD * sizeof(T);          // the CTA's rows
-    static constexpr size_t rows_bytes = (size_t)2 * PB_MAXC * PB_W * sizeof(T);     // pushed candidate rows
-    static constexpr size_t cand_bytes = (size_t)2 * PB_MAXC * 4 * sizeof(unsigned long long);
+    static constexpr size_t rows_bytes = (size_t)PB_MAXC * PB_W * sizeof(T);         // pulled candidate rows
+    static constexpr size_t mine_bytes = (size_t)2 * PB_W * sizeof(T);               // published candidate row (2 parities)
     static constexpr size_t piv_bytes = (size_t)PB_SW * PB_W * sizeof(T);            // the sub-panel's pivot rows
-    static constexpr size_t total = panel_bytes + rows_bytes + cand_bytes + piv_bytes + 64;
+    static constexpr size_t total = panel_bytes + rows_bytes + mine_bytes + piv_bytes + 64;
 };
 
 // Exact arg-max of (key, pos) over a warp: larger key wins, ties -> smaller pos.  Coarse pass
-// on the top 32 bits; the full comparison only among lanes tying on it.
+// on the top 32 bits; the full comparison only among lanes tying on it.  `src` = winning lane.
 template <class KT>
-__device__ __forceinline__ void warp_argmax(KT key, unsigned pos, KT& kbest, unsigned& pbest) {
-    if (sizeof(KT) == 8) {
-        const uint32_t hi = (uint32_t)((unsigned long long)key >> 32);
-        const uint32_t mh = __reduce_max_sync(kFullMask, hi);
-        const unsigned tie = __ballot_sync(kFullMask, hi == mh);
-        if (__popc(tie) == 1) {
-            const int src = __ffs(tie) - 1;
-            kbest = (KT)__shfl_sync(kFullMask, (unsigned long long)key, src);
-            pbest = __shfl_sync(kFullMask, pos, src);
-            return;
+__device__ __forceinline__ void warp_argmax(KT key, unsigned pos, KT& kbest, unsigned& pbest, int& src) {
+    const uint32_t hi = (sizeof(KT) == 8) ? (uint32_t)((unsigned long long)key >> 32) : (uint32_t)key;
+    const uint32_t mh = __reduce_max_sync(kFullMask, hi);
+    unsigned tie = __ballot_sync(kFullMask, hi == mh);
+    if (__popc(tie) != 1) {
+        if (sizeof(KT) == 8) {
+            const uint32_t lo = (hi == mh) ? (uint32_t)key : 0u;
+            const uint32_t ml = __reduce_max_sync(kFullMask, lo);
+            tie = __ballot_sync(kFullMask, (hi == mh) && ((uint32_t)key == ml));
         }
-        const uint32_t lo = (hi == mh) ? (uint32_t)key : 0u;
-        const uint32_t ml = __reduce_max_sync(kFullMask, lo);
-        const bool c = (hi == mh) && ((uint32_t)key == ml);
-        kbest = (KT)(((unsigned long long)mh << 32) | ml);
-        pbest = __reduce_min_sync(kFullMask, c ? pos : 0xffffffffu);
-    } else {
-        const uint32_t k32 = (uint32_t)key;
-        const uint32_t mk = __reduce_max_sync(kFullMask, k32);
-        const unsigned tie = __ballot_sync(kFullMask, k32 == mk);
-        kbest = (KT)mk;
-        if (__popc(tie) == 1) {
-            pbest = __shfl_sync(kFullMask, pos, __ffs(tie) - 1);
-            return;
+        if (__popc(tie) != 1) {
+            const unsigned pm = __reduce_min_sync(kFullMask, ((tie >> (threadIdx.x & 31)) & 1u) ? pos : 0xffffffffu);
+            tie = __ballot_sync(kFullMask, (((tie >> (threadIdx.x & 31)) & 1u) != 0) && pos == pm);
         }
-        pbest = __reduce_min_sync(kFullMask, (k32 == mk) ? pos : 0xffffffffu);
     }
+    src = __ffs(tie) - 1;
+    kbest = (KT)__shfl_sync(kFullMask, (unsigned long long)key, src);
+    pbest = __shfl_sync(kFullMask, pos, src);
 }
 
 template <class T, int RPT>
@@ -95,23 +90,26 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
     constexpr int LD = SM::LD;
     constexpr int W = PB_W, SW = PB_SW;
     struct alignas(16) V16 { T v[VEC]; };
+    static_assert(W == 32, "one lane per panel column in the row copies");
 
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_panel = reinterpret_cast<T*>(smem_raw);                                                 // [PB_ROWS][LD]
-    T* s_rows = reinterpret_cast<T*>(smem_raw + SM::panel_bytes);                                // [2][MAXC][W]
-    unsigned long long* s_cand = reinterpret_cast<unsigned long long*>(smem_raw + SM::panel_bytes + SM::rows_bytes);  // [2][MAXC][4]
-    T* s_piv = reinterpret_cast<T*>(smem_raw + SM::panel_bytes + SM::rows_bytes + SM::cand_bytes);  // [SW][W]
+    T* s_panel = reinterpret_cast<T*>(smem_raw);                                                  // [PB_ROWS][LD]
+    T* s_rows = reinterpret_cast<T*>(smem_raw + SM::panel_bytes);                                 // [MAXC][W] pulled rows
+    T* s_mine = reinterpret_cast<T*>(smem_raw + SM::panel_bytes + SM::rows_bytes);                // [2][W] published row
+    T* s_piv = reinterpret_cast<T*>(smem_raw + SM::panel_bytes + SM::rows_bytes + SM::mine_bytes);  // [SW][W]
+    __shared__ __align__(16) unsigned long long s_pub[2][2];   // published {key, pos} per parity (read remotely)
+    __shared__ __align__(16) unsigned long long s_cand[PB_MAXC][2];  // pulled {key, pos}
+    __shared__ T s_recip[PB_MAXC];
     __shared__ KT s_wkey[NW];
     __shared__ unsigned s_wpos[NW];
     __shared__ int s_wrow[NW];  // local row index (0..PB_ROWS) of each warp's candidate
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // debug phase timing: accumulated in registers, flushed once at the end (a global RMW per
-    // stamp would add an L2 round trip to every phase it tries to measure)
+    // debug phase timing: accumulated in registers, flushed once at the end
     long long tprev = 0, tacc0 = 0, tacc1 = 0, tacc2 = 0, tacc3 = 0, tacc4 = 0, tacc5 = 0, tcols = 0;
     const long long tstart = clock64();
 #define PB_STAMP(slot)                                  \
@@ -131,10 +129,9 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
         for (int c = tid; c < PB_ROWS * CPR; c += TPB) {
             const int r = c / CPR, cc = (c % CPR) * VEC;
             V16 v;
-            if (cta_row0 + r < M) v = *reinterpret_cast<const V16*>(A + (long long)(cta_row0 + r) * lda + cc);
-            else
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) v.v[e] = T(0);
+            for (int e = 0; e < VEC; ++e) v.v[e] = T(0);
+            if (cta_row0 + r < M) v = *reinterpret_cast<const V16*>(A + (long long)(cta_row0 + r) * lda + cc);
             *reinterpret_cast<V16*>(s_panel + r * LD + cc) = v;
         }
     } else {
@@ -150,11 +147,12 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
         const int grow = cta_row0 + tid + r * TPB;
         pos[r] = grow < M ? grow : -1;
     }
+    if (tid < NW) s_wrow[tid] = 0;  // always a valid local row, even before a warp has had a live candidate
     __syncthreads();
-    cluster.sync();  // every CTA of the cluster is running before the first remote store
+    cluster.sync();  // every CTA of the cluster is running before the first remote access
 
     for (int sb = 0; sb < w; sb += SW) {  // sub-panels
-        // ---- sub-panel columns into registers ----
+        // ---- sub-panel columns into the register window ----
         T a[RPT][SW];
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
@@ -167,10 +165,8 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
             }
         }
 
-        // Column steps: a ROLLED loop (the body is compiled once).  The register window slides:
-        // a[r][0] is always the current column, a[r][k] column j+k; the rank-1 update writes its
-        // result one slot down, so the shift costs nothing.  Finished entries (multipliers, and
-        // the U part of a row when it becomes a pivot) go straight to the shared-memory panel.
+        // Column steps: a ROLLED loop (the body is compiled once).  a[r][0] is the current
+        // column, a[r][k] column j+k; the update writes one slot down, so the shift is free.
 #pragma unroll 1
         for (int c = 0; c < SW; ++c) {
             const int j = sb + c;
@@ -178,42 +174,45 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
             const int parity = j & 1;
             const int left = SW - c;  // window entries still inside the sub-panel
             if (timing && rank == 0 && tid == 0) tprev = clock64();
-            T* rows_p = s_rows + parity * (PB_MAXC * W);
-            unsigned long long* cand_p = s_cand + parity * (PB_MAXC * 4);
 
-            // (1) thread candidate over its live rows, then warp candidate
-            KT bkey = 0;
-            unsigned bpos = 0x7fffffffu;
-            int br = 0;
+            // (1) thread candidate over its live rows (keys first, then a compare tree), warp candidate
+            KT key[RPT];
+            unsigned kp[RPT];
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
                 const bool live = pos[r] >= j;
-                const KT key = live ? K::of(a[r][0]) : (KT)0;
-                const unsigned p = live ? (unsigned)pos[r] : 0x7fffffffu;
-                if (key > bkey || (key == bkey && p < bpos)) {
-                    bkey = key;
-                    bpos = p;
-                    br = r;
-                }
+                key[r] = live ? K::of(a[r][0]) : (KT)0;
+                kp[r] = live ? (unsigned)pos[r] : PB_NOPOS;
+            }
+            int br = 0;
+            KT bkey = key[0];
+            unsigned bpos = kp[0];
+#pragma unroll
+            for (int r = 1; r < RPT; ++r) {
+                const bool better = key[r] > bkey || (key[r] == bkey && kp[r] < bpos);
+                bkey = better ? key[r] : bkey;
+                bpos = better ? kp[r] : bpos;
+                br = better ? r : br;
             }
             KT wkey;
             unsigned wpos;
-            warp_argmax<KT>(bkey, bpos, wkey, wpos);
-            if (bpos == wpos && wpos != 0x7fffffffu) {
-                // owner: make its shared-memory row current (columns j .. sb+SW-1 live in the window)
-                const int lrow = tid + br * TPB;
-                T* prow = s_panel + lrow * LD + j;
+            int wsrc;
+            warp_argmax<KT>(bkey, bpos, wkey, wpos, wsrc);
+            if (lane == wsrc) {
+                if (wpos != PB_NOPOS) {
+                    // owner: make its shared-memory row current (columns j .. sb+SW-1 live in the window)
+                    const int lrow = tid + br * TPB;
+                    T* prow = s_panel + lrow * LD + j;
 #pragma unroll
-                for (int r = 0; r < RPT; ++r) {
-                    if (r == br) {
+                    for (int r = 0; r < RPT; ++r) {
+                        if (r == br) {
 #pragma unroll
-                        for (int k = 0; k < SW; ++k)
-                            if (k < left) prow[k] = a[r][k];
+                            for (int k = 0; k < SW; ++k)
+                                if (k < left) prow[k] = a[r][k];
+                        }
                     }
+                    s_wrow[warp] = lrow;
                 }
-                s_wrow[warp] = lrow;
-            }
-            if (lane == 0) {
                 s_wkey[warp] = wkey;
                 s_wpos[warp] = wpos;
             }
@@ -221,70 +220,69 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
             __syncthreads();
             PB_STAMP(1);
 
-            // (2) CTA candidate (every warp, serial over the few warps), pushed to every peer
-            {
-                KT ckey = s_wkey[0];
-                unsigned cpos = s_wpos[0];
-                int cw = 0;
-#pragma unroll
-                for (int i = 1; i < NW; ++i) {
-                    const KT k = s_wkey[i];
-                    const unsigned p = s_wpos[i];
-                    if (k > ckey || (k == ckey && p < cpos)) {
-                        ckey = k;
-                        cpos = p;
-                        cw = i;
-                    }
-                }
-                const T* src = s_panel + s_wrow[cw] * LD;  // garbage index is never used when the CTA has no live row
-                const bool has = (cpos != 0x7fffffffu);
-                for (int peer = warp; peer < C; peer += NW) {
-                    T* dst = cluster.map_shared_rank(rows_p + rank * W, peer);
-                    if (has)
-                        for (int i = lane; i < W; i += 32) dst[i] = src[i];
-                    if (lane == 0) {
-                        unsigned long long* dc = cluster.map_shared_rank(cand_p + rank * 4, peer);
-                        T rc = T(0);
-                        if (has && ckey != 0) rc = T(1) / src[j];  // A::one() / pivot (getrf.rs:76)
-                        unsigned long long rbits;
-                        if (sizeof(T) == 8) rbits = (unsigned long long)__double_as_longlong((double)rc);
-                        else rbits = (unsigned long long)__float_as_uint((float)rc);
-                        dc[0] = (unsigned long long)ckey;
-                        dc[1] = (unsigned long long)cpos;
-                        dc[2] = rbits;
-                    }
+            // (2) warp 0: CTA candidate -> published in this CTA's own shared memory
+            if (warp == 0) {
+                const KT k = lane < NW ? s_wkey[lane] : (KT)0;
+                const unsigned p = lane < NW ? s_wpos[lane] : PB_NOPOS;
+                KT ckey;
+                unsigned cpos;
+                int cw;
+                warp_argmax<KT>(k, p, ckey, cpos, cw);
+                const int lrow = s_wrow[cw < NW ? cw : 0];
+                s_mine[parity * W + lane] = s_panel[lrow * LD + lane];  // garbage when the CTA has no live row: never selected
+                if (lane == 0) {
+                    s_pub[parity][0] = (unsigned long long)ckey;
+                    s_pub[parity][1] = (unsigned long long)cpos;
                 }
             }
             PB_STAMP(2);
             cluster.sync();
             PB_STAMP(3);
 
-            // (3) every warp picks the same winner among the C candidates in its own shared memory
+            // (3) pull: warp wq fetches the record and the row of peers wq, wq+NW, ... (all loads in flight
+            //     together); the lane that holds column j also forms the reciprocal of that candidate
+            {
+                constexpr int Q = (PB_MAXC + NW - 1) / NW;
+                T v[Q];
+                unsigned long long rec[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {  // unconditional loads (own CTA stands in for absent peers)
+                    const int peer = warp + q * NW;
+                    const int pc = peer < C ? peer : rank;
+                    v[q] = cluster.map_shared_rank(s_mine + parity * W, pc)[lane];
+                    rec[q] = cluster.map_shared_rank(&s_pub[parity][0], pc)[lane & 1];
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const int peer = warp + q * NW;
+                    const T rc = T(1) / v[q];  // A::one() / pivot (getrf.rs:76); only lane j's value is kept
+                    if (peer < C) {
+                        s_rows[peer * W + lane] = v[q];
+                        if (lane < 2) s_cand[peer][lane] = rec[q];
+                        if (lane == j) s_recip[peer] = rc;
+                    }
+                }
+            }
+            __syncthreads();
+            // every warp picks the same winner among the C candidates now in its own shared memory
             KT gkey;
             unsigned gpos_u;
+            int gw;
             {
-                const KT k = lane < C ? (KT)cand_p[lane * 4 + 0] : (KT)0;
-                const unsigned p = lane < C ? (unsigned)cand_p[lane * 4 + 1] : 0x7fffffffu;
-                warp_argmax<KT>(k, p, gkey, gpos_u);
+                const KT k = lane < C ? (KT)s_cand[lane][0] : (KT)0;
+                const unsigned p = lane < C ? (unsigned)s_cand[lane][1] : PB_NOPOS;
+                warp_argmax<KT>(k, p, gkey, gpos_u, gw);
             }
-            // the winning CTA = the lane whose candidate position equals gpos (positions are unique)
-            const unsigned mine = lane < C ? (unsigned)cand_p[lane * 4 + 1] : 0xffffffffu;
-            const int gw = __ffs(__ballot_sync(kFullMask, mine == gpos_u)) - 1;
             const int gpos = (int)gpos_u;
             const bool sing = (gkey == 0);
-            const T* urow = rows_p + gw * W;
+            const T* urow = s_rows + gw * W;
             if (rank == 0 && tid == 0) {
                 ipiv[j] = row_base + gpos;
                 if (sing) *info = step_base + j;  // last zero-pivot step wins (getrf.rs:72-73)
             }
-            if (warp == 0) s_piv[c * W + lane] = urow[lane];  // keep the pivot row for the block update (W == 32)
+            if (warp == NW - 1) s_piv[c * W + lane] = urow[lane];  // keep the pivot row for the block update
             PB_STAMP(4);
-            T recip = T(0);
-            if (!sing) {
-                const unsigned long long rbits = cand_p[gw * 4 + 2];
-                if (sizeof(T) == 8) recip = (T)__longlong_as_double((long long)rbits);
-                else recip = (T)__uint_as_float((unsigned)rbits);
-            }
+            const T recip = sing ? T(0) : s_recip[gw];
             T u[SW];  // u[k] = pivot-row entry of column j+k (zero beyond the sub-panel)
 #pragma unroll
             for (int k = 1; k < SW; ++k) u[k] = (k < left) ? urow[j + k] : T(0);
@@ -315,9 +313,8 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
 
         const int c1 = sb + SW;           // first parked column
         const int npark = W - c1;         // parked columns still to update (multiple of 8, may be 0)
-        const int kdone = (w - sb) < SW ? (w - sb) : SW;  // pivots found in this sub-panel
-        if (npark > 0 && c1 < w) {
-            __syncthreads();  // s_piv rows complete (written by warp 0 during the column steps)
+        if (npark > 0 && c1 < w) {        // (then all SW pivots of this sub-panel exist)
+            __syncthreads();  // s_piv rows complete
             // U12 = L11^-1 * P12 by forward substitution, one thread per parked column (tiny)
             if (tid < npark) {
                 T uc[SW];
@@ -325,10 +322,8 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 for (int i = 0; i < SW; ++i) uc[i] = s_piv[i * W + c1 + tid];
 #pragma unroll
                 for (int i = 1; i < SW; ++i) {
-                    if (i < kdone) {
 #pragma unroll
-                        for (int k = 0; k < i; ++k) uc[i] -= s_piv[i * W + sb + k] * uc[k];
-                    }
+                    for (int k = 0; k < i; ++k) uc[i] -= s_piv[i * W + sb + k] * uc[k];
                 }
 #pragma unroll
                 for (int i = 0; i < SW; ++i) s_piv[i * W + c1 + tid] = uc[i];
@@ -339,10 +334,10 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
             for (int r = 0; r < RPT; ++r) {
                 T* prow = s_panel + (tid + r * TPB) * LD;
                 const int p = pos[r];
-                if (p >= sb && p < sb + kdone) {
+                if (p >= sb && p < sb + SW) {
                     const T* urow12 = s_piv + (p - sb) * W;
                     for (int k = c1; k < W; k += VEC) *reinterpret_cast<V16*>(prow + k) = *reinterpret_cast<const V16*>(urow12 + k);
-                } else if (p >= sb + kdone) {
+                } else if (p >= sb + SW) {
                     T lm[SW];  // this row's 8 multipliers of the sub-panel
 #pragma unroll
                     for (int cc = 0; cc < SW / VEC; ++cc) {
@@ -350,6 +345,7 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) lm[cc * VEC + e] = v.v[e];
                     }
+#pragma unroll 2
                     for (int k = c1; k < W; k += VEC) {
                         V16 x = *reinterpret_cast<const V16*>(prow + k);
 #pragma unroll
@@ -366,7 +362,7 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
         }
     }
 
-    // ---- rows to their final positions: a warp per row, coalesced ----
+    // ---- rows to their final positions ----
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
@@ -452,9 +448,9 @@ template <class T>
 int panel_blocked_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info,
                       int32_t step_base, cudaStream_t s) {
     if (w > PB_W || rows > (int64_t)PB_MAXC * PB_ROWS) return LAIR_B200_ERR_UNSUPPORTED;
-    if (ctx().opt.panel_rpt == 2) return launch_blocked<T, 2>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
-    if (ctx().opt.panel_rpt == 8) return launch_blocked<T, 8>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
-    return launch_blocked<T, 4>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+    if (ctx().opt.panel_rpt == 1) return launch_blocked<T, 1>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+    if (ctx().opt.panel_rpt == 4) return launch_blocked<T, 4>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+    return launch_blocked<T, 2>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
 }
 
 int panel_blocked_timing(long long* out8, bool clear) {

@@ -145,7 +145,7 @@ def sec_panel():
             a = a0.clone()
             ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
             info = torch.empty(1, dtype=torch.int32, device="cuda")
-            for cl, grp, rpt in ((2, 4, 2), (2, 4, 4), (2, 4, 8), (1, 4, 4), (0, 4, 4)):
+            for cl, grp, rpt in ((2, 4, 1), (2, 4, 2), (2, 4, 4), (1, 4, 2), (0, 4, 2)):
                 _ffi.set_option("panel_cluster", cl)
                 _ffi.set_option("panel_group", grp)
                 _ffi.set_option("panel_rpt", rpt)
@@ -154,7 +154,7 @@ def sec_panel():
                 out(bench=f"{pfx}panel", cluster=cl, group=grp, rpt=rpt, m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
             _ffi.set_option("panel_cluster", 2)
             _ffi.set_option("panel_group", 4)
-            _ffi.set_option("panel_rpt", 4)
+            _ffi.set_option("panel_rpt", 2)
 
 
 def sec_paneltiming():
