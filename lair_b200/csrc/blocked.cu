@@ -18,53 +18,88 @@ struct Factor {
     int64_t lda, m, n;
     int32_t* ipiv;
     int32_t* info;
-    cudaStream_t s;
+    cudaStream_t s;  // the caller's stream: everything is ordered after / visible on it
 
     T* at(int64_t r, int64_t c) const { return A + r * lda + c; }
 
     // columns [c0, c1) of the whole matrix get the interchanges ipiv[k0..k1)
-    int swap_cols(int64_t c0, int64_t c1, int64_t k0, int64_t k1) const {
+    int swap_cols(int64_t c0, int64_t c1, int64_t k0, int64_t k1, cudaStream_t st) const {
         if (c1 <= c0 || k1 <= k0) return LAIR_B200_OK;
-        return laswp_dev<T>(c1 - c0, A + c0, lda, k0, k1, ipiv, s);
+        return laswp_dev<T>(c1 - c0, A + c0, lda, k0, k1, ipiv, st);
     }
 
     // factor columns [j0, j0+w) below (and including) row j0; earlier columns' updates applied
-    int rec(int64_t j0, int64_t w) const {
+    int rec(int64_t j0, int64_t w, cudaStream_t st) const {
         const int64_t rows = m - j0;
         const int wp = panel_max_width<T>(rows);
         if (wp <= 0) {
             set_error("getrf: %lld rows exceed the on-chip panel capacity", (long long)rows);
             return LAIR_B200_ERR_UNSUPPORTED;
         }
-        if (w <= wp) return panel_dev<T>(rows, w, at(j0, j0), lda, ipiv + j0, (int32_t)j0, info, (int32_t)j0, s);
+        if (w <= wp) return panel_dev<T>(rows, w, at(j0, j0), lda, ipiv + j0, (int32_t)j0, info, (int32_t)j0, st);
         int64_t w1 = (w / 2 + wp - 1) / wp * wp;  // left half, a multiple of the panel width
         if (w1 >= w) w1 = w - wp > 0 ? (w - 1) / wp * wp : wp;
-        LAIR_CHECK(rec(j0, w1));
+        LAIR_CHECK(rec(j0, w1, st));
         const int64_t c0 = j0 + w1, c1 = j0 + w;
-        LAIR_CHECK(swap_cols(c0, c1, j0, j0 + w1));                                       // laswp  (getrf.rs:270-277)
-        LAIR_CHECK(trsm_lower_unit_dev<T>(w1, c1 - c0, at(j0, j0), lda, at(j0, c0), lda, s));  // trsm   (:278-283)
+        LAIR_CHECK(swap_cols(c0, c1, j0, j0 + w1, st));                                        // laswp  (getrf.rs:270-277)
+        LAIR_CHECK(trsm_lower_unit_dev<T>(w1, c1 - c0, at(j0, j0), lda, at(j0, c0), lda, st));  // trsm   (:278-283)
         if (m > c0)
-            LAIR_CHECK(gemm_minus_dev<T>(m - c0, c1 - c0, w1, at(c0, j0), lda, at(j0, c0), lda, at(c0, c0), lda, s));  // gemm (:289-296)
-        LAIR_CHECK(rec(c0, c1 - c0));                                                     // recurse (:297)
-        return swap_cols(j0, c0, c0, c1);                                                 // laswp left (:308-315)
+            LAIR_CHECK(gemm_minus_dev<T>(m - c0, c1 - c0, w1, at(c0, j0), lda, at(j0, c0), lda, at(c0, c0), lda, st));  // gemm (:289-296)
+        LAIR_CHECK(rec(c0, c1 - c0, st));                                                      // recurse (:297)
+        return swap_cols(j0, c0, c0, c1, st);                                                  // laswp left (:308-315)
     }
 
+    // trailing update of columns [c0, c1) with the factored block [j0, j0+jb)
+    int update(int64_t j0, int64_t jb, int64_t c0, int64_t c1, cudaStream_t st) const {
+        if (c1 <= c0) return LAIR_B200_OK;
+        const int64_t r1 = j0 + jb;
+        LAIR_CHECK(swap_cols(c0, c1, j0, r1, st));
+        LAIR_CHECK(trsm_lower_unit_dev<T>(jb, c1 - c0, at(j0, j0), lda, at(j0, c0), lda, st));
+        if (r1 < m) LAIR_CHECK(gemm_minus_dev<T>(m - r1, c1 - c0, jb, at(r1, j0), lda, at(j0, c0), lda, at(r1, c0), lda, st));
+        return LAIR_B200_OK;
+    }
+
+    // Right-looking sweep with one block of lookahead: the panel path of block k+1 (stream P,
+    // high priority) runs under the bulk of block k's trailing update (stream M).
+    //   M: wait panel(k) | left laswp | update(next block) -> EN | update(rest)
+    //   P: wait EN | rec(next block) -> EP
+    // The two streams only ever touch disjoint column ranges (P: the next block; M: the rest and
+    // the already-factored left part) and disjoint ipiv ranges.
     int run() const {
         const int64_t kmin = m < n ? m : n;
         set_i32_kernel<<<1, 1, 0, s>>>(info, -1);
         LAIR_LAUNCH_CHECK();
         const int64_t nb = ctx().opt.nb;
+        const bool look = ctx().opt.lookahead != 0 && kmin > nb;
+        cudaStream_t M = s, P = look ? ctx().aux_stream : s;
+        cudaEvent_t EP = ctx().ev[0], EN = ctx().ev[1];
+        if (look) {
+            LAIR_CUDA_CHECK(cudaEventRecord(EN, M));  // P starts after everything already queued on the caller's stream
+            LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+        }
+        LAIR_CHECK(rec(0, kmin < nb ? kmin : nb, P));
         for (int64_t j0 = 0; j0 < kmin; j0 += nb) {
             const int64_t jb = (kmin - j0) < nb ? (kmin - j0) : nb;
-            LAIR_CHECK(rec(j0, jb));
-            LAIR_CHECK(swap_cols(0, j0, j0, j0 + jb));  // interchanges reach back into L
-            const int64_t c0 = j0 + jb;
-            if (c0 < n) {
-                LAIR_CHECK(swap_cols(c0, n, j0, j0 + jb));
-                LAIR_CHECK(trsm_lower_unit_dev<T>(jb, n - c0, at(j0, j0), lda, at(j0, c0), lda, s));
-                if (c0 < m)
-                    LAIR_CHECK(gemm_minus_dev<T>(m - c0, n - c0, jb, at(c0, j0), lda, at(j0, c0), lda, at(c0, c0), lda, s));
+            const int64_t c0 = j0 + jb;                      // first column right of the block
+            const int64_t nb2 = (c0 < kmin) ? ((kmin - c0) < nb ? (kmin - c0) : nb) : 0;  // width of the next block to factor
+            if (look) {
+                LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
+                LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
             }
+            if (nb2 > 0) {
+                LAIR_CHECK(update(j0, jb, c0, c0 + nb2, M));  // next block first ...
+                if (look) {
+                    LAIR_CUDA_CHECK(cudaEventRecord(EN, M));
+                    LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+                }
+                LAIR_CHECK(rec(c0, nb2, P));                  // ... so its panel path can start under the rest
+            }
+            LAIR_CHECK(update(j0, jb, c0 + nb2, n, M));
+            LAIR_CHECK(swap_cols(0, j0, j0, j0 + jb, M));     // interchanges reach back into L (off the critical path)
+        }
+        if (look) {  // the caller's stream sees the last panel too (already implied, kept explicit)
+            LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
+            LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
         }
         return LAIR_B200_OK;
     }

@@ -125,15 +125,16 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
     const int cta_row0 = rank * PB_ROWS;
     const bool vec_ok = (w == W) && ((lda % VEC) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     if (vec_ok) {
+        // cp.async: every 16-byte chunk of the CTA's 128 KB slab is in flight at once (zero-filled past row M)
         constexpr int CPR = W / VEC;
         for (int c = tid; c < PB_ROWS * CPR; c += TPB) {
             const int r = c / CPR, cc = (c % CPR) * VEC;
-            V16 v;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) v.v[e] = T(0);
-            if (cta_row0 + r < M) v = *reinterpret_cast<const V16*>(A + (long long)(cta_row0 + r) * lda + cc);
-            *reinterpret_cast<V16*>(s_panel + r * LD + cc) = v;
+            const bool in = cta_row0 + r < M;
+            const T* src = A + (long long)(in ? cta_row0 + r : 0) * lda + cc;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_panel + r * LD + cc);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
         }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
     } else {
         for (int idx = tid; idx < PB_ROWS * W; idx += TPB) {
             const int r = idx / W, c = idx % W;

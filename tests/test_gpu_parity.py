@@ -234,7 +234,7 @@ def test_blocked_f64_matches_oracle(lair, shape):
     assert be <= 10 * max(be_o, 0.01), (be, be_o)
 
 
-@pytest.mark.parametrize("option,values", [("panel_cluster", (0, 1, 2)), ("panel_rpt", (1, 4, 2)), ("gemm_cfg", (1, 2, 3, 0)),
+@pytest.mark.parametrize("option,values", [("panel_cluster", (0, 1, 2)), ("panel_rpt", (1, 4, 2)), ("lookahead", (0, 1)), ("gemm_cfg", (1, 2, 3, 0)),
                                            ("nb", (64, 128, 512, 256))])
 def test_blocked_f64_kernel_variants(lair, option, values):
     """Every kernel variant behind a tuning option produces the oracle's pivots and L\\U."""

@@ -195,9 +195,12 @@ def sec_paneltiming():
 def sec_getrf():
     for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
         fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
-        for n in (1024, 2048, 4096, 8192):
-            for nb in (128, 256, 512):
+        for n in (2048, 4096, 8192, 16384):
+            if n == 16384 and pfx == "s":
+                continue
+            for nb, look in ((128, 1), (256, 1), (512, 1), (256, 0)):
                 _ffi.set_option("nb", nb)
+                _ffi.set_option("lookahead", look)
                 a0 = torch.rand(n, n, dtype=dt, device="cuda") * 10
                 a = a0.clone()
                 ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -218,9 +221,10 @@ def sec_getrf():
                 rec = (torch.tril(LU, -1) + torch.eye(n, dtype=torch.float64, device="cuda")) @ torch.triu(LU)
                 eps = (2.0 ** -53) if dt == torch.float64 else (2.0 ** -24)
                 be = float(torch.linalg.norm(PA - rec) / (n * eps * torch.linalg.norm(PA)))
-                out(bench=f"{pfx}getrf", n=n, nb=nb, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9, launches=launches,
-                    backward_error=be, info=int(info.item()))
+                out(bench=f"{pfx}getrf", n=n, nb=nb, lookahead=look, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9,
+                    launches=launches, backward_error=be, info=int(info.item()))
         _ffi.set_option("nb", 256)
+        _ffi.set_option("lookahead", 1)
 
 
 def sec_getrs():
