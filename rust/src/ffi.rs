@@ -1,0 +1,33 @@
+//! Raw bindings of include/lair_b200.h (the C ABI of the CUDA library).
+#![allow(non_camel_case_types)]
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+extern "C" {
+    pub fn lair_b200_last_error() -> *const c_char;
+    pub fn lair_b200_init(device: c_int) -> c_int;
+    pub fn lair_b200_shutdown() -> c_int;
+
+    pub fn lair_b200_sgetrf(m: i64, n: i64, a: *mut f32, rs: i64, cs: i64, ipiv: *mut i64, info: *mut i64) -> c_int;
+    pub fn lair_b200_dgetrf(m: i64, n: i64, a: *mut f64, rs: i64, cs: i64, ipiv: *mut i64, info: *mut i64) -> c_int;
+    pub fn lair_b200_cgetrf(m: i64, n: i64, a: *mut c_void, rs: i64, cs: i64, ipiv: *mut i64, info: *mut i64) -> c_int;
+    pub fn lair_b200_zgetrf(m: i64, n: i64, a: *mut c_void, rs: i64, cs: i64, ipiv: *mut i64, info: *mut i64) -> c_int;
+
+    pub fn lair_b200_sgetrs(n: i64, nrhs: i64, lu: *const f32, lu_rs: i64, lu_cs: i64, ipiv: *const i64,
+                            b: *const f32, b_rs: i64, b_cs: i64, x: *mut f32, x_rs: i64, x_cs: i64) -> c_int;
+    pub fn lair_b200_dgetrs(n: i64, nrhs: i64, lu: *const f64, lu_rs: i64, lu_cs: i64, ipiv: *const i64,
+                            b: *const f64, b_rs: i64, b_cs: i64, x: *mut f64, x_rs: i64, x_cs: i64) -> c_int;
+    pub fn lair_b200_cgetrs(n: i64, nrhs: i64, lu: *const c_void, lu_rs: i64, lu_cs: i64, ipiv: *const i64,
+                            b: *const c_void, b_rs: i64, b_cs: i64, x: *mut c_void, x_rs: i64, x_cs: i64) -> c_int;
+    pub fn lair_b200_zgetrs(n: i64, nrhs: i64, lu: *const c_void, lu_rs: i64, lu_cs: i64, ipiv: *const i64,
+                            b: *const c_void, b_rs: i64, b_cs: i64, x: *mut c_void, x_rs: i64, x_cs: i64) -> c_int;
+}
+
+/// The reference signatures have no error channel for runtime failure, so a non-zero status
+/// (no device, CUDA error, allocation failure) becomes a panic carrying the library's message.
+pub(crate) fn check(status: c_int) {
+    if status != 0 {
+        let msg = unsafe { CStr::from_ptr(lair_b200_last_error()) }.to_string_lossy().into_owned();
+        panic!("lair_b200 status {status}: {msg}");
+    }
+}
