@@ -127,6 +127,20 @@ LAIR_B200_API int lair_b200_strsm_dev(int64_t k, int64_t ncols, const float* d_l
 LAIR_B200_API int lair_b200_dgemm_minus_dev(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, const double* d_b, int64_t ldb, double* d_c, int64_t ldc, void* stream);
 LAIR_B200_API int lair_b200_sgemm_minus_dev(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc, void* stream);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink --------------------------
+ * One large LU on a 1-D block-cyclic COLUMN distribution: global block column j (width nb)
+ * lives on rank j mod P as local block j / P; d_a_local is n rows x local_cols, row-major with
+ * leading dimension lda.  Per block column the owner factors the panel and broadcasts the packed
+ * panel + nb pivots (ncclBroadcast); every rank updates its own columns; one block of lookahead.
+ * d_ipiv (n int32, replicated on every rank) and d_info as in getrf_dev.
+ * Communicator set-up: rank 0 calls mg_unique_id (128 bytes), the host layer distributes the
+ * bytes (torch.distributed or any other channel), every rank calls mg_init. */
+LAIR_B200_API int lair_b200_mg_unique_id(void* id128);
+LAIR_B200_API int lair_b200_mg_init(int rank, int nranks, const void* id128);
+LAIR_B200_API int lair_b200_mg_finalize(void);
+LAIR_B200_API int lair_b200_dgetrf_mg_dev(int64_t n, int64_t nb, double* d_a_local, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
+LAIR_B200_API int lair_b200_sgetrf_mg_dev(int64_t n, int64_t nb, float* d_a_local, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
+
 /* Tuning knobs (also read from the environment at init: LAIR_B200_NB, LAIR_B200_SMALL_N).
  * name in {"nb", "small_n", "lookahead"}; returns LAIR_B200_ERR_INVALID for unknown names. */
 LAIR_B200_API int lair_b200_set_option(const char* name, int64_t value);

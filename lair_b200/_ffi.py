@@ -37,6 +37,11 @@ _SIGNATURES = {
     "lair_b200_get_option": [ctypes.c_char_p, ctypes.POINTER(i64)],
     "lair_b200_launch_count": [],
     "lair_b200_debug_panel_timing": [ctypes.POINTER(ctypes.c_longlong), cint],
+    "lair_b200_mg_unique_id": [vp],
+    "lair_b200_mg_init": [cint, cint, vp],
+    "lair_b200_mg_finalize": [],
+    "lair_b200_dgetrf_mg_dev": [i64, i64, vp, i64, vp, vp, vp],
+    "lair_b200_sgetrf_mg_dev": [i64, i64, vp, i64, vp, vp, vp],
     "lair_b200_profile_begin": [],
     "lair_b200_profile_end": [],
     "lair_b200_profile_get": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),

@@ -28,26 +28,29 @@ struct Factor {
         return laswp_dev<T>(c1 - c0, A + c0, lda, k0, k1, ipiv, st);
     }
 
-    // factor columns [j0, j0+w) below (and including) row j0; earlier columns' updates applied
-    int rec(int64_t j0, int64_t w, cudaStream_t st) const {
-        const int64_t rows = m - j0;
+    // Factor the w columns stored at (local) columns [c0, c0+w), whose diagonal starts at row r0:
+    // rows r0..m participate, pivots land in ipiv[r0..r0+w).  On one GPU c0 == r0; under the
+    // block-cyclic column distribution (mg.cu) c0 is the block's local column offset.
+    int rec(int64_t r0, int64_t c0, int64_t w, cudaStream_t st) const {
+        const int64_t rows = m - r0;
         const int wp = panel_max_width<T>(rows);
         if (wp <= 0) {
             set_error("getrf: %lld rows exceed the on-chip panel capacity", (long long)rows);
             return LAIR_B200_ERR_UNSUPPORTED;
         }
-        if (w <= wp) return panel_dev<T>(rows, w, at(j0, j0), lda, ipiv + j0, (int32_t)j0, info, (int32_t)j0, st);
+        if (w <= wp) return panel_dev<T>(rows, w, at(r0, c0), lda, ipiv + r0, (int32_t)r0, info, (int32_t)r0, st);
         int64_t w1 = (w / 2 + wp - 1) / wp * wp;  // left half, a multiple of the panel width
         if (w1 >= w) w1 = w - wp > 0 ? (w - 1) / wp * wp : wp;
-        LAIR_CHECK(rec(j0, w1, st));
-        const int64_t c0 = j0 + w1, c1 = j0 + w;
-        LAIR_CHECK(swap_cols(c0, c1, j0, j0 + w1, st));                                        // laswp  (getrf.rs:270-277)
-        LAIR_CHECK(trsm_lower_unit_dev<T>(w1, c1 - c0, at(j0, j0), lda, at(j0, c0), lda, st));  // trsm   (:278-283)
-        if (m > c0)
-            LAIR_CHECK(gemm_minus_dev<T>(m - c0, c1 - c0, w1, at(c0, j0), lda, at(j0, c0), lda, at(c0, c0), lda, st));  // gemm (:289-296)
-        LAIR_CHECK(rec(c0, c1 - c0, st));                                                      // recurse (:297)
-        return swap_cols(j0, c0, c0, c1, st);                                                  // laswp left (:308-315)
+        LAIR_CHECK(rec(r0, c0, w1, st));
+        const int64_t r1 = r0 + w1, cr = c0 + w1, w2 = w - w1;
+        LAIR_CHECK(swap_cols(cr, cr + w2, r0, r1, st));                                           // laswp  (getrf.rs:270-277)
+        LAIR_CHECK(trsm_lower_unit_dev<T>(w1, w2, at(r0, c0), lda, at(r0, cr), lda, st));         // trsm   (:278-283)
+        if (m > r1)
+            LAIR_CHECK(gemm_minus_dev<T>(m - r1, w2, w1, at(r1, c0), lda, at(r0, cr), lda, at(r1, cr), lda, st));  // gemm (:289-296)
+        LAIR_CHECK(rec(r1, cr, w2, st));                                                          // recurse (:297)
+        return swap_cols(c0, cr, r1, r0 + w, st);                                                 // laswp left (:308-315)
     }
+    int rec(int64_t j0, int64_t w, cudaStream_t st) const { return rec(j0, j0, w, st); }
 
     // trailing update of columns [c0, c1) with the factored block [j0, j0+jb)
     int update(int64_t j0, int64_t jb, int64_t c0, int64_t c1, cudaStream_t st) const {
@@ -116,6 +119,17 @@ int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv
     Factor<T> f{d_a, lda, m, n, d_ipiv, d_info, s};
     return f.run();
 }
+
+// Factor one block column of a (possibly column-distributed) matrix: the w columns stored at local
+// columns [c0, c0+w) of d_a (m rows, leading dimension lda), diagonal starting at row r0.
+template <class T>
+int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r0, int64_t c0, int64_t w, int32_t* d_ipiv, int32_t* d_info,
+                    cudaStream_t s) {
+    Factor<T> f{d_a, lda, m, c0 + w, d_ipiv, d_info, s};
+    return f.rec(r0, c0, w, s);
+}
+template int getrf_block_dev<float>(int64_t, float*, int64_t, int64_t, int64_t, int64_t, int32_t*, int32_t*, cudaStream_t);
+template int getrf_block_dev<double>(int64_t, double*, int64_t, int64_t, int64_t, int64_t, int32_t*, int32_t*, cudaStream_t);
 
 // X = U^-1 L^-1 P B, in place in d_b (n x nrhs row-major): getrs.rs:22-36 for every column.
 template <class T>

@@ -198,7 +198,7 @@ def sec_getrf():
         for n in (2048, 4096, 8192, 16384):
             if n == 16384 and pfx == "s":
                 continue
-            for nb, look in ((128, 1), (256, 1), (512, 1), (256, 0)):
+            for nb, look in ((64, 1), (96, 1), (128, 1), (192, 1), (256, 1), (256, 0)):
                 _ffi.set_option("nb", nb)
                 _ffi.set_option("lookahead", look)
                 a0 = torch.rand(n, n, dtype=dt, device="cuda") * 10
