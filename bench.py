@@ -497,8 +497,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lair_b200", choices=["lair_b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
-    ap.add_argument("--n", type=int, default=65536, help="matrix order of the c4 workload")
-    ap.add_argument("--nb", type=int, default=256, help="block-cyclic block width of the c4 workload")
+    ap.add_argument("--order", dest="n", type=int, default=65536, help="matrix order n of the c4 workload")
+    ap.add_argument("--block", dest="nb", type=int, default=256, help="block-cyclic block width of the c4 workload")
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--ref-n", type=int, default=2048, help="sample size of the CPU (oracle) leg")
     ap.add_argument("--no-e2e", action="store_true")
