@@ -18,8 +18,11 @@ flops/step = 2/3 n^3 + 2 n^2 nrhs.
 * `--impl reference`: times the reference's CPU algorithm (oracle port; the reference is Rust
              and cannot be built in this image) on the host cores; same JSON shape.
 
-N>1 ranks (torchrun) run independent systems of the same shape (weak scaling, no data-path
-collective); `--workload c3` benches the batched 32x32 path (mats/s), sharded by batch.
+N>1 ranks (torchrun) default to `--workload c4`: ONE f64 LU of order 65536 (BASELINE configs[3]) on
+a 1-D block-cyclic column distribution, NCCL panel/pivot broadcast with lookahead (strong scaling;
+value = 2/3 n^3 / time, also reported as a fraction of N x 37.0 TFLOP/s).  `--workload c2` under
+torchrun runs independent n = 8192 systems per rank (weak scaling, no collective); `--workload c3`
+benches the batched 32x32 path (mats/s), sharded by batch.
 """
 from __future__ import annotations
 
@@ -177,7 +180,9 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": "getrf_f64_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10)",
-        "config": {"workload": f"c2 getrf+getrs f64 n={N_C2} nrhs={NRHS_C2} (bounded sample n={args.ref_n})", "inputs": "host"},
+        "config": {"workload": (f"c2 getrf+getrs f64 n={N_C2} nrhs={NRHS_C2}" if world == 1 else f"c4 getrf f64 n={args.n}") +
+                               f" (bounded sample: n={args.ref_n} getrf + {NRHS_C2} getrs; the reference is O(n^3) scalar code, "
+                               "n=8192 would take minutes and n=65536 ~35 h on one core)", "inputs": "host"},
         "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -496,7 +501,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lair_b200", choices=["lair_b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4"],
+                    help="default: c2 on one GPU, c4 (one n=65536 LU distributed over the ranks) on several")
     ap.add_argument("--order", dest="n", type=int, default=65536, help="matrix order n of the c4 workload")
     ap.add_argument("--block", dest="nb", type=int, default=256, help="block-cyclic block width of the c4 workload")
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
@@ -512,6 +518,8 @@ def main():
         world = int(os.environ.get("WORLD_SIZE", "1"))
         run_reference(args, rank, world)
         return
+    if args.workload is None:
+        args.workload = "c2" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c4"
     rank, world, local = _dist_setup(args.gpus, force=(args.workload == "c4"))
     try:
         if args.workload == "c2":
