@@ -85,17 +85,19 @@ batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __re
         for (int j = 0; j < N; ++j) {
             if (!FULL && j >= n) break;
             // -- iamax over logical rows >= j (iamax.rs:10-19) --
+            // strict `>` in the reference == lowest logical row among equal maxima; one REDUX + one
+            // vote on the top 32 bits of |x| decide it unless lanes tie there (pivot_key.cuh)
             const bool live = pos >= j;
-            typename K::type key = live ? K::of(a[j]) : (typename K::type)0;
-            typename K::type kmax = K::warp_max(key);
+            const typename K::type key = live ? K::of(a[j]) : (typename K::type)0;
+            typename K::type kmax;
+            unsigned ppos;
+            int wl;
+            warp_argmax<typename K::type>(key, live ? (unsigned)pos : 0x7fffffffu, kmax, ppos, wl);
             if (kmax == 0) {  // max_val == 0: singular step, no swap, no update (getrf.rs:72-73)
                 sing = j;
                 continue;
             }
-            const bool cand = live && (key == kmax);
-            // strict `>` in the reference == lowest logical row among equal maxima
-            const unsigned ppos = __reduce_min_sync(kFull, cand ? (unsigned)pos : 0xffffffffu);
-            const bool is_w = cand && ((unsigned)pos == ppos);
+            const bool is_w = (lane == wl);
             if (lane == j) mypiv = (int)ppos;
             if (pos == j) pos = (int)ppos;  // the row sitting at j moves to the pivot's old place
             if (is_w) pos = j;              // the pivot row moves to j
@@ -113,20 +115,21 @@ batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __re
                 }
             }
             __syncwarp();
-            T u[N];
-#pragma unroll
-            for (int c = c0; c < CPR; ++c) {
-                V v = *reinterpret_cast<const V*>(rb + c * VEC);
-                const T* pv = reinterpret_cast<const T*>(&v);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) u[c * VEC + e] = pv[e];
-            }
-            const T recip = O::recip(u[j]);  // A::one() / pivot (getrf.rs:76)
+            const T recip = O::recip(rb[j]);  // A::one() / pivot (getrf.rs:76)
             if (pos > j) {
                 const T l = O::mul(a[j], recip);  // *row_j *= pivot_recip (getrf.rs:81)
                 a[j] = l;
+                // the pivot row is consumed chunk by chunk straight from shared memory (no register copy)
 #pragma unroll
-                for (int k = j + 1; k < N; ++k) a[k] = O::sub(a[k], O::mul(l, u[k]));  // getrf.rs:86-87
+                for (int c = (j + 1) / VEC; c < CPR; ++c) {
+                    const V v = *reinterpret_cast<const V*>(rb + c * VEC);
+                    const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const int k = c * VEC + e;
+                        if (k > j) a[k] = O::sub(a[k], O::mul(l, pv[e]));  // getrf.rs:86-87
+                    }
+                }
             }
         }
 

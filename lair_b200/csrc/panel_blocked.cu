@@ -54,28 +54,7 @@ struct PBSmem {
     static constexpr size_t total = panel_bytes + rows_bytes + mine_bytes + piv_bytes + 64;
 };
 
-// Exact arg-max of (key, pos) over a warp: larger key wins, ties -> smaller pos.  Coarse pass
-// on the top 32 bits; the full comparison only among lanes tying on it.  `src` = winning lane.
-template <class KT>
-__device__ __forceinline__ void warp_argmax(KT key, unsigned pos, KT& kbest, unsigned& pbest, int& src) {
-    const uint32_t hi = (sizeof(KT) == 8) ? (uint32_t)((unsigned long long)key >> 32) : (uint32_t)key;
-    const uint32_t mh = __reduce_max_sync(kFullMask, hi);
-    unsigned tie = __ballot_sync(kFullMask, hi == mh);
-    if (__popc(tie) != 1) {
-        if (sizeof(KT) == 8) {
-            const uint32_t lo = (hi == mh) ? (uint32_t)key : 0u;
-            const uint32_t ml = __reduce_max_sync(kFullMask, lo);
-            tie = __ballot_sync(kFullMask, (hi == mh) && ((uint32_t)key == ml));
-        }
-        if (__popc(tie) != 1) {
-            const unsigned pm = __reduce_min_sync(kFullMask, ((tie >> (threadIdx.x & 31)) & 1u) ? pos : 0xffffffffu);
-            tie = __ballot_sync(kFullMask, (((tie >> (threadIdx.x & 31)) & 1u) != 0) && pos == pm);
-        }
-    }
-    src = __ffs(tie) - 1;
-    kbest = (KT)__shfl_sync(kFullMask, (unsigned long long)key, src);
-    pbest = __shfl_sync(kFullMask, pos, src);
-}
+// warp_argmax (exact, coarse-key first) lives in pivot_key.cuh.
 
 template <class T, int RPT>
 __global__ void __launch_bounds__(PB_ROWS / RPT, 1)
