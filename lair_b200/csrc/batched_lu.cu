@@ -28,7 +28,9 @@ template <class T> struct Vec16;  // 16-byte vector of T
 template <> struct Vec16<float> { using type = float4; static constexpr int n = 4; };
 template <> struct Vec16<double> { using type = double2; static constexpr int n = 2; };
 
-template <class T, int WARPS, int MINB, bool FULL>
+// VAR bit 0: coarse-key arg-max (1 REDUX + vote) instead of full-key REDUX chain;
+// VAR bit 1: consume the pivot row chunk by chunk from shared memory instead of a register copy.
+template <class T, int WARPS, int MINB, bool FULL, int VAR>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __restrict__ info, long long batch, int n) {
     constexpr int N = 32;
@@ -91,13 +93,21 @@ batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __re
             const typename K::type key = live ? K::of(a[j]) : (typename K::type)0;
             typename K::type kmax;
             unsigned ppos;
-            int wl;
-            warp_argmax<typename K::type>(key, live ? (unsigned)pos : 0x7fffffffu, kmax, ppos, wl);
+            bool is_w;
+            if constexpr ((VAR & 1) != 0) {
+                int wl;
+                warp_argmax<typename K::type>(key, live ? (unsigned)pos : 0x7fffffffu, kmax, ppos, wl);
+                is_w = (lane == wl);
+            } else {
+                kmax = K::warp_max(key);
+                const bool cand = live && (key == kmax);
+                ppos = __reduce_min_sync(kFull, cand ? (unsigned)pos : 0xffffffffu);
+                is_w = cand && ((unsigned)pos == ppos);
+            }
             if (kmax == 0) {  // max_val == 0: singular step, no swap, no update (getrf.rs:72-73)
                 sing = j;
                 continue;
             }
-            const bool is_w = (lane == wl);
             if (lane == j) mypiv = (int)ppos;
             if (pos == j) pos = (int)ppos;  // the row sitting at j moves to the pivot's old place
             if (is_w) pos = j;              // the pivot row moves to j
@@ -115,20 +125,38 @@ batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __re
                 }
             }
             __syncwarp();
-            const T recip = O::recip(rb[j]);  // A::one() / pivot (getrf.rs:76)
-            if (pos > j) {
-                const T l = O::mul(a[j], recip);  // *row_j *= pivot_recip (getrf.rs:81)
-                a[j] = l;
-                // the pivot row is consumed chunk by chunk straight from shared memory (no register copy)
+            if constexpr ((VAR & 2) != 0) {
+                const T recip = O::recip(rb[j]);  // A::one() / pivot (getrf.rs:76)
+                if (pos > j) {
+                    const T l = O::mul(a[j], recip);  // *row_j *= pivot_recip (getrf.rs:81)
+                    a[j] = l;
+                    // the pivot row is consumed chunk by chunk straight from shared memory (no register copy)
 #pragma unroll
-                for (int c = (j + 1) / VEC; c < CPR; ++c) {
-                    const V v = *reinterpret_cast<const V*>(rb + c * VEC);
+                    for (int c = (j + 1) / VEC; c < CPR; ++c) {
+                        const V v = *reinterpret_cast<const V*>(rb + c * VEC);
+                        const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            const int k = c * VEC + e;
+                            if (k > j) a[k] = O::sub(a[k], O::mul(l, pv[e]));  // getrf.rs:86-87
+                        }
+                    }
+                }
+            } else {
+                T u[N];
+#pragma unroll
+                for (int c = c0; c < CPR; ++c) {
+                    V v = *reinterpret_cast<const V*>(rb + c * VEC);
                     const T* pv = reinterpret_cast<const T*>(&v);
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const int k = c * VEC + e;
-                        if (k > j) a[k] = O::sub(a[k], O::mul(l, pv[e]));  // getrf.rs:86-87
-                    }
+                    for (int e = 0; e < VEC; ++e) u[c * VEC + e] = pv[e];
+                }
+                const T recip = O::recip(u[j]);  // A::one() / pivot (getrf.rs:76)
+                if (pos > j) {
+                    const T l = O::mul(a[j], recip);  // *row_j *= pivot_recip (getrf.rs:81)
+                    a[j] = l;
+#pragma unroll
+                    for (int k = j + 1; k < N; ++k) a[k] = O::sub(a[k], O::mul(l, u[k]));  // getrf.rs:86-87
                 }
             }
         }
@@ -162,10 +190,10 @@ batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __re
     }
 }
 
-template <class T, int WARPS, int MINB, bool FULL>
+template <class T, int WARPS, int MINB, bool FULL, int VAR>
 int launch_batched(long long batch, int n, T* d_a, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s) {
     constexpr int N = 32, VEC = Vec16<T>::n, LD = N + VEC;
-    auto kern = batched_lu32_kernel<T, WARPS, MINB, FULL>;
+    auto kern = batched_lu32_kernel<T, WARPS, MINB, FULL, VAR>;
     size_t smem = (size_t)WARPS * (N * LD + 2 * LD) * sizeof(T);
     static bool configured = false;
     static int blocks_per_sm = 1;
@@ -194,16 +222,23 @@ int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t
     if (batch == 0 || n == 0) return LAIR_B200_OK;
     LAIR_REQUIRE(d_a && d_ipiv && d_info, "batched getrf: null pointer");
     const bool full = (n == 32) && (reinterpret_cast<uintptr_t>(d_a) % 16 == 0);
-    // Occupancy variants: fewer registers (small spills) vs fewer resident warps; the
-    // default was picked on a B200 (profiles/), LAIR_B200_BATCHED_CFG=1 selects the other.
-    constexpr int kLo = sizeof(T) == 8 ? 3 : 5;  // no spills
-    constexpr int kHi = sizeof(T) == 8 ? 4 : 8;  // max occupancy
+    // Tuning variants (option "batched_cfg", bit field): bit 0 = tighter register bound (more resident
+    // warps), bit 1 = coarse-key arg-max, bit 2 = pivot row consumed from shared memory.  The default
+    // was picked on a B200 (profiles/r1_batched_ncu.md).
+    constexpr int kLo = sizeof(T) == 8 ? 3 : 5;
+    constexpr int kHi = sizeof(T) == 8 ? 4 : 8;
     const int64_t cfg = ctx().opt.batched_cfg;
-    if (full) {
-        if (cfg == 1) return launch_batched<T, 4, kHi, true>(batch, 32, d_a, d_ipiv, d_info, s);
-        return launch_batched<T, 4, kLo, true>(batch, 32, d_a, d_ipiv, d_info, s);
+    if (!full) return launch_batched<T, 4, kLo, false, 0>(batch, (int)n, d_a, d_ipiv, d_info, s);
+    switch (cfg & 7) {
+        case 1: return launch_batched<T, 4, kHi, true, 0>(batch, 32, d_a, d_ipiv, d_info, s);
+        case 2: return launch_batched<T, 4, kLo, true, 1>(batch, 32, d_a, d_ipiv, d_info, s);
+        case 3: return launch_batched<T, 4, kHi, true, 1>(batch, 32, d_a, d_ipiv, d_info, s);
+        case 4: return launch_batched<T, 4, kLo, true, 2>(batch, 32, d_a, d_ipiv, d_info, s);
+        case 5: return launch_batched<T, 4, kHi, true, 2>(batch, 32, d_a, d_ipiv, d_info, s);
+        case 6: return launch_batched<T, 4, kLo, true, 3>(batch, 32, d_a, d_ipiv, d_info, s);
+        case 7: return launch_batched<T, 4, kHi, true, 3>(batch, 32, d_a, d_ipiv, d_info, s);
+        default: return launch_batched<T, 4, kLo, true, 0>(batch, 32, d_a, d_ipiv, d_info, s);
     }
-    return launch_batched<T, 4, kLo, false>(batch, (int)n, d_a, d_ipiv, d_info, s);
 }
 
 template int getrf_batched_dev<float>(int64_t, int64_t, float*, int32_t*, int32_t*, cudaStream_t);
