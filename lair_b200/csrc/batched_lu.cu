@@ -51,6 +51,13 @@ batched_lu32_kernel(T* __restrict__ A, int32_t* __restrict__ ipiv, int32_t* __re
 
     for (long long mi = warp_global; mi < batch; mi += warp_total) {
         T* g = A + mi * (long long)n * n;
+        // pull this warp's NEXT matrix into L2 while the current one is factored (there is no room
+        // for a second shared-memory buffer without losing resident warps)
+        if (FULL && mi + warp_total < batch) {
+            const char* nxt = reinterpret_cast<const char*>(A + (mi + warp_total) * (long long)N * N);
+            for (int off = lane * 128; off < (int)(N * N * sizeof(T)); off += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(nxt + off));
+        }
         // ---- stage the matrix: coalesced global -> padded shared ----
         if (FULL) {
 #pragma unroll
@@ -227,7 +234,8 @@ int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t
     // was picked on a B200 (profiles/r1_batched_ncu.md).
     constexpr int kLo = sizeof(T) == 8 ? 3 : 5;
     constexpr int kHi = sizeof(T) == 8 ? 4 : 8;
-    const int64_t cfg = ctx().opt.batched_cfg;
+    int64_t cfg = ctx().opt.batched_cfg;
+    if (cfg < 0) cfg = sizeof(T) == 8 ? 5 : 0;  // measured best on B200: f64 130.7 M/s (cfg 5), f32 239.6 M/s (cfg 0)
     if (!full) return launch_batched<T, 4, kLo, false, 0>(batch, (int)n, d_a, d_ipiv, d_info, s);
     switch (cfg & 7) {
         case 1: return launch_batched<T, 4, kHi, true, 0>(batch, 32, d_a, d_ipiv, d_info, s);

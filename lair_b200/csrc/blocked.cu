@@ -72,7 +72,11 @@ struct Factor {
         const int64_t kmin = m < n ? m : n;
         set_i32_kernel<<<1, 1, 0, s>>>(info, -1);
         LAIR_LAUNCH_CHECK();
-        const int64_t nb = ctx().opt.nb;
+        // outer block width: with lookahead the factorization is bound by the panel path up to
+        // n ~ 8192 (narrow blocks keep it short) and by the trailing GEMM beyond (wide blocks feed
+        // the DMMA kernel with a deeper K); measured on B200, profiles/r1_bench_history.md
+        int64_t nb = ctx().opt.nb;
+        if (nb <= 0) nb = kmin <= 10240 ? 64 : (kmin <= 14336 ? 128 : 256);
         const bool look = ctx().opt.lookahead != 0 && kmin > nb;
         cudaStream_t M = s, P = look ? ctx().aux_stream : s;
         cudaEvent_t EP = ctx().ev[0], EN = ctx().ev[1];

@@ -130,10 +130,10 @@ template <class R> struct Ops<cx<R>> {
 
 // ---- process-wide context ----------------------------------------------------------------
 struct Options {
-    int64_t nb = 256;        // outer block width of the blocked factorization
+    int64_t nb = 0;          // outer block width of the blocked factorization (0 = chosen from the matrix order)
     int64_t small_n = 128;   // max(m, n) handled by the single-CTA exact kernel
     int64_t lookahead = 1;   // overlap panel k+1 with trailing update k
-    int64_t batched_cfg = 0; // occupancy variant of the batched kernel (batched_lu.cu)
+    int64_t batched_cfg = -1; // tuning variant of the batched kernel, -1 = measured best per type (batched_lu.cu)
     int64_t panel_cluster = 2;  // panels that fit one cluster: 2 blocked DSMEM kernel, 1 row-per-thread DSMEM kernel, 0 global-memory exchange
     int64_t panel_rpt = 2;      // rows per thread of the blocked cluster panel kernel (1, 2, 4)
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)

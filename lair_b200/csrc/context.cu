@@ -158,8 +158,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
     if (!name) return LAIR_B200_ERR_INVALID;
     Options& o = g_ctx.opt;
     if (!strcmp(name, "nb")) {
-        if (value < 32 || value % 32) {
-            set_error("nb must be a positive multiple of 32, got %lld", (long long)value);
+        if (value != 0 && (value < 32 || value % 32)) {
+            set_error("nb must be 0 (automatic) or a positive multiple of 32, got %lld", (long long)value);
             return LAIR_B200_ERR_INVALID;
         }
         o.nb = value;

@@ -139,6 +139,28 @@ sgemm_minus_kernel(const float* __restrict__ A, long long lda, const float* __re
     }
     cp_async_wait<0>();
     const bool vec_ok = ALIGNED && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    if (vec_ok && m0 + BM <= M && n0 + BN <= N) {
+        // interior tile: all 16 loads of the C fragment in flight before the first use (a conditional
+        // per element serialises one DRAM latency per load -- profiles/r1_dgemm_ncu.md)
+        float* cbase = C + (long long)(m0 + ty) * ldc + n0 + tx * 4;
+        float4 cv[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) cv[i][h] = *reinterpret_cast<const float4*>(cbase + (long long)(16 * i) * ldc + h * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 v = cv[i][h];
+                v.x -= acc[i][h * 4 + 0];
+                v.y -= acc[i][h * 4 + 1];
+                v.z -= acc[i][h * 4 + 2];
+                v.w -= acc[i][h * 4 + 3];
+                *reinterpret_cast<float4*>(cbase + (long long)(16 * i) * ldc + h * 64) = v;
+            }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         int row = m0 + ty + 16 * i;

@@ -133,7 +133,7 @@ def sec_batched():
                                reps=5, setup=lambda: a.copy_(a0))
             out(bench=f"{pfx}getrf_batched32", cfg=cfg, batch=batch, ms_best=best, ms_med=med, mats_per_s=batch / best * 1e3,
                 gbs=batch * bpm / best * 1e-6, frac_of_6453=batch * bpm / best * 1e-6 / 6453.7)
-        _ffi.set_option("batched_cfg", 0)
+        _ffi.set_option("batched_cfg", -1)
 
 
 def sec_panel():
@@ -223,7 +223,7 @@ def sec_getrf():
                 be = float(torch.linalg.norm(PA - rec) / (n * eps * torch.linalg.norm(PA)))
                 out(bench=f"{pfx}getrf", n=n, nb=nb, lookahead=look, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9,
                     launches=launches, backward_error=be, info=int(info.item()))
-        _ffi.set_option("nb", 256)
+        _ffi.set_option("nb", 0)
         _ffi.set_option("lookahead", 1)
 
 
