@@ -184,6 +184,8 @@ template <class T> int panel_max_width(int64_t rows);
 template <class T> int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 int panel_cluster_max_rows();
 int panel_cluster_timing(long long* out8, bool clear);
+// 32x32 batched LU, two matrices per warp (batched_lu2.cu)
+template <class T> int getrf_batched32x2_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // factor one block column stored at local columns [c0, c0+w), diagonal at row r0 (blocked.cu)
 template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r0, int64_t c0, int64_t w, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
 // in-kernel blocked cluster panel (panel_blocked.cu): 8-column register sub-panels, RPT rows per thread

@@ -43,6 +43,32 @@ def test_batched32_bit_exact(lair, dt, dist):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_batched32_every_variant_bit_exact(lair, dt, cfg):
+    """Every tuning variant of the batched kernel (incl. two matrices per warp, odd batch, ties,
+    singular and NaN inputs) is bit-identical to the oracle."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(100 + cfg)
+    a0 = _rand(rng, (1001, 32, 32), dt)
+    a0[5] = rng.integers(-2, 3, size=(32, 32)).astype(dt)
+    a0[6] = 0
+    a0[7, :, 3] = 0
+    a0[8, 4, 4] = np.nan
+    a0[1000] = 1
+    ref = a0.copy()
+    piv_o, info_o = oracle.getrf_batched(ref)
+    try:
+        _ffi.set_option("batched_cfg", cfg)
+        a = a0.copy()
+        ipiv, info = lair.lapack.getrf_batched(a)
+    finally:
+        _ffi.set_option("batched_cfg", -1)
+    assert np.array_equal(ipiv, piv_o.astype(np.int32))
+    assert np.array_equal(info, info_o.astype(np.int32))
+    assert np.array_equal(a, ref, equal_nan=True)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [1, 2, 5, 17, 31])
 def test_batched_small_n_bit_exact(lair, dt, n):
     rng = np.random.default_rng(n)
