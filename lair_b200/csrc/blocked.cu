@@ -28,6 +28,19 @@ struct Factor {
         return laswp_dev<T>(c1 - c0, A + c0, lda, k0, k1, ipiv, st);
     }
 
+    // laswp(ipiv[k0..k0+k)) on columns [c0, c1), then the unit-lower solve of their rows k0..k0+k
+    // against the k x k block at (k0, lc0): one fused launch for narrow blocks, else laswp + trsm.
+    int swap_solve(int64_t k0, int64_t k, int64_t lc0, int64_t c0, int64_t c1, cudaStream_t st) const {
+        if (c1 <= c0 || k <= 0) return LAIR_B200_OK;
+        const int64_t fuse = ctx().opt.fuse_swap_trsm;
+        if (fuse == 1 || (fuse == 2 && c1 - c0 <= 512)) {
+            const int rc = laswp_trsm_dev<T>(c1 - c0, A + c0, lda, k0, k, ipiv, at(k0, lc0), lda, st);
+            if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
+        }
+        LAIR_CHECK(swap_cols(c0, c1, k0, k0 + k, st));                                            // laswp  (getrf.rs:270-277)
+        return trsm_lower_unit_dev<T>(k, c1 - c0, at(k0, lc0), lda, at(k0, c0), lda, st);         // trsm   (:278-283)
+    }
+
     // Factor the w columns stored at (local) columns [c0, c0+w), whose diagonal starts at row r0:
     // rows r0..m participate, pivots land in ipiv[r0..r0+w).  On one GPU c0 == r0; under the
     // block-cyclic column distribution (mg.cu) c0 is the block's local column offset.
@@ -43,8 +56,7 @@ struct Factor {
         if (w1 >= w) w1 = w - wp > 0 ? (w - 1) / wp * wp : wp;
         LAIR_CHECK(rec(r0, c0, w1, st));
         const int64_t r1 = r0 + w1, cr = c0 + w1, w2 = w - w1;
-        LAIR_CHECK(swap_cols(cr, cr + w2, r0, r1, st));                                           // laswp  (getrf.rs:270-277)
-        LAIR_CHECK(trsm_lower_unit_dev<T>(w1, w2, at(r0, c0), lda, at(r0, cr), lda, st));         // trsm   (:278-283)
+        LAIR_CHECK(swap_solve(r0, w1, c0, cr, cr + w2, st));                                      // laswp + trsm
         if (m > r1)
             LAIR_CHECK(gemm_minus_dev<T>(m - r1, w2, w1, at(r1, c0), lda, at(r0, cr), lda, at(r1, cr), lda, st));  // gemm (:289-296)
         LAIR_CHECK(rec(r1, cr, w2, st));                                                          // recurse (:297)
@@ -56,8 +68,7 @@ struct Factor {
     int update(int64_t j0, int64_t jb, int64_t c0, int64_t c1, cudaStream_t st) const {
         if (c1 <= c0) return LAIR_B200_OK;
         const int64_t r1 = j0 + jb;
-        LAIR_CHECK(swap_cols(c0, c1, j0, r1, st));
-        LAIR_CHECK(trsm_lower_unit_dev<T>(jb, c1 - c0, at(j0, j0), lda, at(j0, c0), lda, st));
+        LAIR_CHECK(swap_solve(j0, jb, j0, c0, c1, st));
         if (r1 < m) LAIR_CHECK(gemm_minus_dev<T>(m - r1, c1 - c0, jb, at(r1, j0), lda, at(j0, c0), lda, at(r1, c0), lda, st));
         return LAIR_B200_OK;
     }

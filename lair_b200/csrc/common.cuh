@@ -138,6 +138,7 @@ struct Options {
     int64_t panel_rpt = 2;      // rows per thread of the blocked cluster panel kernel (1, 2, 4)
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
+    int64_t fuse_swap_trsm = 1; // block steps of width <= 64: one fused laswp+trsm launch (laswp_trsm.cu)
     int64_t trsm_dataflow = 1;  // f64 getrs: persistent dataflow triangular solves (trsm_dataflow.cu)
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
 };
@@ -184,6 +185,8 @@ template <class T> int panel_max_width(int64_t rows);
 template <class T> int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 int panel_cluster_max_rows();
 int panel_cluster_timing(long long* out8, bool clear);
+// fused laswp + unit-lower trsm for k <= 64 (laswp_trsm.cu); LAIR_B200_ERR_UNSUPPORTED beyond
+template <class T> int laswp_trsm_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k, const int32_t* d_ipiv, const T* d_l, int64_t ldl, cudaStream_t s);
 // 32x32 batched LU, two matrices per warp (batched_lu2.cu)
 template <class T> int getrf_batched32x2_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // factor one block column stored at local columns [c0, c0+w), diagonal at row r0 (blocked.cu)

@@ -1,0 +1,150 @@
+// Fused row interchange + unit-lower triangular solve for one block step of the factorization:
+//     A[:, cols]  <-  laswp(ipiv[k0 .. k0+k))           (src/lapack/laswp.rs:11-40)
+//     A[k0..k0+k, cols]  <-  L11^-1 * A[k0..k0+k, cols]  (src/blas/trsm.rs:6-22)
+// i.e. the laswp + trsm pair of the blocked LU (reference shape: src/lapack/getrf.rs:270-283) in
+// ONE launch for k <= 64.  On the lookahead's critical path the two used to be 2-4 dependent
+// latency-bound launches (~12 us each); fused, the moved rows are gathered once, the top k rows are
+// solved in shared memory, and everything is scattered once.
+//
+// One CTA per strip of COLS columns.  The k sequential transpositions are collapsed into row moves
+// exactly as in laswp.cu; rows that land in the top block [k0, k0+k) are loaded into the `top`
+// tile (by destination), rows that leave it into the `far` buffer.  HBM traffic: each touched row
+// segment read once and written once.
+#include "common.cuh"
+
+namespace lair {
+namespace {
+
+constexpr int LT_KMAX = 64;
+constexpr int LT_THREADS = 256;
+
+template <class T>
+struct LtCfg {
+    static constexpr int COLS = 32;             // columns per CTA
+    static constexpr int LDT = COLS + 1;        // top / far tile pitch
+    static constexpr int LDL = LT_KMAX + 1;     // L tile pitch
+    static constexpr size_t smem_bytes = (size_t)(2 * LT_KMAX * LDT + LT_KMAX * LDL) * sizeof(T);
+};
+
+template <class T>
+__global__ void __launch_bounds__(LT_THREADS)
+laswp_trsm_kernel(T* __restrict__ A, long long lda, int ncols, int k0, int k, const int32_t* __restrict__ ipiv,
+                  const T* __restrict__ L, long long ldl) {
+    using C = LtCfg<T>;
+    constexpr int COLS = C::COLS, LDT = C::LDT, LDL = C::LDL;
+    __shared__ int s_piv[LT_KMAX];
+    __shared__ int s_topsrc[LT_KMAX];        // source row of each top destination row
+    __shared__ int s_farsrc[LT_KMAX];        // moves that leave the top block: source (a top row) ...
+    __shared__ int s_fardst[LT_KMAX];        // ... and destination (a far row)
+    __shared__ int s_nfar;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* top = reinterpret_cast<T*>(smem_raw);     // [k][LDT]
+    T* far = top + LT_KMAX * LDT;                // [nfar][LDT]
+    T* Ls = far + LT_KMAX * LDT;                 // [k][LDL]
+
+    const int tid = threadIdx.x;
+    const int col0 = blockIdx.x * COLS;
+    const int cw = (ncols - col0) < COLS ? (ncols - col0) : COLS;  // columns of this strip
+
+    if (tid < k) {
+        s_piv[tid] = ipiv[k0 + tid];
+        s_topsrc[tid] = k0 + tid;
+    }
+    if (tid == 0) s_nfar = 0;
+    // the triangle (strictly lower part of L11; unit diagonal implied)
+    for (int idx = tid; idx < k * k; idx += LT_THREADS) {
+        const int r = idx / k, c = idx - r * k;
+        Ls[r * LDL + c] = (c < r) ? L[(long long)r * ldl + c] : T(0);
+    }
+    __syncthreads();
+    // ---- collapse the k transpositions (k0+i <-> s_piv[i]) into row moves (same scheme as laswp.cu) ----
+    if (tid < 2 * k) {
+        int src = -1;
+        if (tid < k) {
+            src = k0 + tid;
+        } else {
+            const int u = tid - k;
+            const int r = s_piv[u];
+            if (r >= k0 + k) {  // a far row; take it once (first occurrence)
+                bool dup = false;
+                for (int v = 0; v < u; ++v) dup |= (s_piv[v] == r);
+                if (!dup) src = r;
+            }
+        }
+        if (src >= 0) {
+            int cur = src;
+            for (int i = 0; i < k; ++i) {
+                const int ri = k0 + i, p = s_piv[i];
+                if (cur == ri) cur = p;
+                else if (cur == p) cur = ri;
+            }
+            if (cur < k0 + k) {
+                s_topsrc[cur - k0] = src;            // lands in the top block (possibly unmoved)
+            } else if (cur != src) {
+                const int e = atomicAdd(&s_nfar, 1);  // leaves the top block
+                s_farsrc[e] = src;
+                s_fardst[e] = cur;
+            }
+        }
+    }
+    __syncthreads();
+    const int nfar = s_nfar;
+    // ---- gather: every source row segment read before anything is written ----
+    for (int idx = tid; idx < k * COLS; idx += LT_THREADS) {
+        const int i = idx / COLS, c = idx - i * COLS;
+        if (c < cw) top[i * LDT + c] = A[(long long)s_topsrc[i] * lda + col0 + c];
+    }
+    for (int idx = tid; idx < nfar * COLS; idx += LT_THREADS) {
+        const int e = idx / COLS, c = idx - e * COLS;
+        if (c < cw) far[e * LDT + c] = A[(long long)s_farsrc[e] * lda + col0 + c];
+    }
+    __syncthreads();
+    // ---- unit-lower solve of the top tile, column sweep: row i -= L[i][kk] * row kk ----
+    for (int kk = 0; kk + 1 < k; ++kk) {
+        const int rem = k - kk - 1;
+        for (int idx = tid; idx < rem * COLS; idx += LT_THREADS) {
+            const int i = kk + 1 + idx / COLS, c = idx % COLS;
+            top[i * LDT + c] -= Ls[i * LDL + kk] * top[kk * LDT + c];
+        }
+        __syncthreads();
+    }
+    // ---- scatter ----
+    for (int idx = tid; idx < k * COLS; idx += LT_THREADS) {
+        const int i = idx / COLS, c = idx - i * COLS;
+        if (c < cw) A[(long long)(k0 + i) * lda + col0 + c] = top[i * LDT + c];
+    }
+    for (int idx = tid; idx < nfar * COLS; idx += LT_THREADS) {
+        const int e = idx / COLS, c = idx - e * COLS;
+        if (c < cw) A[(long long)s_fardst[e] * lda + col0 + c] = far[e * LDT + c];
+    }
+}
+
+}  // namespace
+
+// d_a points at row 0 of the matrix and the first of the `ncols` columns to update; the pivots
+// ipiv[k0 .. k0+k) are absolute row indices; d_l is the k x k unit-lower block (leading dimension ldl).
+// Returns LAIR_B200_ERR_UNSUPPORTED (no error text) when k > 64: callers fall back to laswp + trsm.
+template <class T>
+int laswp_trsm_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k, const int32_t* d_ipiv, const T* d_l, int64_t ldl,
+                   cudaStream_t s) {
+    if (k > LT_KMAX) return LAIR_B200_ERR_UNSUPPORTED;
+    if (ncols <= 0 || k <= 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(ncols < (1ll << 31) && k0 + k < (1ll << 31), "laswp_trsm: dimension too large");
+    auto kern = laswp_trsm_kernel<T>;
+    const size_t smem = LtCfg<T>::smem_bytes;
+    static bool configured = false;
+    if (!configured) {
+        LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const unsigned grid = (unsigned)((ncols + LtCfg<T>::COLS - 1) / LtCfg<T>::COLS);
+    ProfScope prof(kProfLaswp, s, 4.0 * (double)k * (double)ncols * sizeof(T));
+    kern<<<grid, LT_THREADS, smem, s>>>(d_a, (long long)lda, (int)ncols, (int)k0, (int)k, d_ipiv, d_l, (long long)ldl);
+    LAIR_LAUNCH_CHECK();
+    return LAIR_B200_OK;
+}
+
+template int laswp_trsm_dev<float>(int64_t, float*, int64_t, int64_t, int64_t, const int32_t*, const float*, int64_t, cudaStream_t);
+template int laswp_trsm_dev<double>(int64_t, double*, int64_t, int64_t, int64_t, const int32_t*, const double*, int64_t, cudaStream_t);
+
+}  // namespace lair

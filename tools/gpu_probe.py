@@ -227,6 +227,25 @@ def sec_getrf():
         _ffi.set_option("lookahead", 1)
 
 
+def sec_fuse():
+    """dgetrf/sgetrf with the fused laswp+trsm launch off / narrow-only / everywhere."""
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for n in (4096, 8192):
+            a0 = torch.rand(n, n, dtype=dt, device="cuda") * 10
+            a = a0.clone()
+            ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+            info = torch.empty(1, dtype=torch.int32, device="cuda")
+            for fuse in (0, 2, 1):
+                _ffi.set_option("fuse_swap_trsm", fuse)
+                l0 = _ffi.launch_count()
+                best, med = timeit(lambda: _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream())),
+                                   reps=5, warm=1, setup=lambda: a.copy_(a0))
+                out(bench=f"{pfx}getrf_fuse", n=n, fuse=fuse, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9,
+                    launches=(_ffi.launch_count() - l0) // 6, checksum=float(a.double().abs().sum()), piv_sum=int(ipiv.sum()))
+    _ffi.set_option("fuse_swap_trsm", 1)
+
+
 def sec_getrs():
     for dt, pfx in ((torch.float64, "d"),):
         n, nrhs = 8192, 64
