@@ -138,6 +138,7 @@ struct Options {
     int64_t panel_rpt = 2;      // rows per thread of the blocked cluster panel kernel (1, 2, 4)
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
+    int64_t panel_exchange = 1; // panel_blocked: 1 = st.async record push + winner-row pull, 0 = cluster barrier + pull
     int64_t fuse_swap_trsm = 1; // block steps of width <= 64: one fused laswp+trsm launch (laswp_trsm.cu)
     int64_t trsm_dataflow = 1;  // f64 getrs: persistent dataflow triangular solves (trsm_dataflow.cu)
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)

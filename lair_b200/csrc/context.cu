@@ -183,6 +183,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.trsm_dataflow = value;
     } else if (!strcmp(name, "fuse_swap_trsm")) {
         o.fuse_swap_trsm = value;
+    } else if (!strcmp(name, "panel_exchange")) {
+        o.panel_exchange = value;
     } else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;
@@ -204,6 +206,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "panel_timing")) *value = o.panel_timing;
     else if (!strcmp(name, "trsm_dataflow")) *value = o.trsm_dataflow;
     else if (!strcmp(name, "fuse_swap_trsm")) *value = o.fuse_swap_trsm;
+    else if (!strcmp(name, "panel_exchange")) *value = o.panel_exchange;
     else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;

@@ -56,7 +56,31 @@ struct PBSmem {
 
 // warp_argmax (exact, coarse-key first) lives in pivot_key.cuh.
 
-template <class T, int RPT>
+// ---- st.async exchange helpers (ASYNC variant) ----
+__device__ __forceinline__ unsigned pb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned pb_mapa(unsigned addr, unsigned cta_rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void pb_mbar_wait_cluster(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+
+// ASYNC = false: candidates published locally, one cluster barrier per column, peers PULL records
+//                and rows (second generation of the exchange).
+// ASYNC = true : every CTA PUSHES its 16-byte candidate record to all peers with st.async
+//                (completion counted by the receiver's mbarrier: no cluster barrier in the column
+//                loop; 448 vs ~1900 cycles for 16 CTAs, profiles/r1_latbench_b200.jsonl), each warp
+//                then decides the winner from its own shared memory and pulls only the winner's row.
+template <class T, int RPT, bool ASYNC>
 __global__ void __launch_bounds__(PB_ROWS / RPT, 1)
 panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __restrict__ ipiv, int row_base,
                      int32_t* __restrict__ info, int step_base, int timing) {
@@ -81,7 +105,9 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
     T* s_mine = reinterpret_cast<T*>(smem_raw + SM::panel_bytes + SM::rows_bytes);                // [2][W] published row
     T* s_piv = reinterpret_cast<T*>(smem_raw + SM::panel_bytes + SM::rows_bytes + SM::mine_bytes);  // [SW][W]
     __shared__ __align__(16) unsigned long long s_pub[2][2];   // published {key, pos} per parity (read remotely)
-    __shared__ __align__(16) unsigned long long s_cand[PB_MAXC][2];  // pulled {key, pos}
+    __shared__ __align__(16) unsigned long long s_cand[2][PB_MAXC][2];  // pulled (parity 0 only) or pushed {key, pos}
+    __shared__ __align__(8) unsigned long long s_mbar[2];               // ASYNC: one mbarrier per column parity
+    __shared__ __align__(16) unsigned long long s_win[2];               // ASYNC: the column's winner {key, pos}
     __shared__ T s_recip[PB_MAXC];
     __shared__ KT s_wkey[NW];
     __shared__ unsigned s_wpos[NW];
@@ -128,6 +154,11 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
         pos[r] = grow < M ? grow : -1;
     }
     if (tid < NW) s_wrow[tid] = 0;  // always a valid local row, even before a warp has had a live candidate
+    if (ASYNC && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_u32(&s_mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pb_smem_u32(&s_mbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     cluster.sync();  // every CTA of the cluster is running before the first remote access
 
@@ -210,12 +241,54 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 warp_argmax<KT>(k, p, ckey, cpos, cw);
                 const int lrow = s_wrow[cw < NW ? cw : 0];
                 s_mine[parity * W + lane] = s_panel[lrow * LD + lane];  // garbage when the CTA has no live row: never selected
-                if (lane == 0) {
+                if constexpr (ASYNC) {
+                    const unsigned bar = pb_smem_u32(&s_mbar[parity]);
+                    if (lane == 0) {  // arm this column's phase: C records of 16 bytes will land here
+                        unsigned long long st_;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(st_) : "r"(bar), "r"((unsigned)C * 16u) : "memory");
+                    }
+                    __syncwarp();  // the row above is written before any peer can learn of the record
+                    if (lane < C) {
+                        const unsigned raddr = pb_mapa(pb_smem_u32(&s_cand[parity][rank][0]), (unsigned)lane);
+                        const unsigned rbar = pb_mapa(bar, (unsigned)lane);
+                        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+                                     "l"((unsigned long long)ckey), "l"((unsigned long long)cpos), "r"(rbar)
+                                     : "memory");
+                    }
+                } else if (lane == 0) {
                     s_pub[parity][0] = (unsigned long long)ckey;
                     s_pub[parity][1] = (unsigned long long)cpos;
                 }
             }
             PB_STAMP(2);
+            KT gkey;
+            unsigned gpos_u;
+            int gw;
+            const T* urow;
+            T recip_w;  // 1 / pivot (getrf.rs:76)
+            if constexpr (ASYNC) {
+                // (3a) warp 0 waits for the C records, decides the winner and pulls the winner's row: ONE
+                //      remote request per CTA (128 warps pulling from one SM cost ~1200 cycles, measured)
+                if (warp == 0) {
+                    pb_mbar_wait_cluster(pb_smem_u32(&s_mbar[parity]), (unsigned)(j >> 1) & 1u);
+                    PB_STAMP(3);
+                    const KT k = lane < C ? (KT)s_cand[parity][lane][0] : (KT)0;
+                    const unsigned p = lane < C ? (unsigned)s_cand[parity][lane][1] : PB_NOPOS;
+                    warp_argmax<KT>(k, p, gkey, gpos_u, gw);
+                    const T v = cluster.map_shared_rank(s_mine + parity * W, gw < C ? gw : rank)[lane];
+                    s_rows[lane] = v;
+                    s_piv[c * W + lane] = v;  // keep the pivot row for the block update
+                    if (lane == 0) {
+                        s_win[0] = (unsigned long long)gkey;
+                        s_win[1] = (unsigned long long)gpos_u;
+                    }
+                }
+                __syncthreads();
+                gkey = (KT)s_win[0];
+                gpos_u = (unsigned)s_win[1];
+                urow = s_rows;
+                recip_w = T(1) / urow[j];
+            } else {
             cluster.sync();
             PB_STAMP(3);
 
@@ -238,31 +311,30 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                     const T rc = T(1) / v[q];  // A::one() / pivot (getrf.rs:76); only lane j's value is kept
                     if (peer < C) {
                         s_rows[peer * W + lane] = v[q];
-                        if (lane < 2) s_cand[peer][lane] = rec[q];
+                        if (lane < 2) s_cand[0][peer][lane] = rec[q];
                         if (lane == j) s_recip[peer] = rc;
                     }
                 }
             }
             __syncthreads();
             // every warp picks the same winner among the C candidates now in its own shared memory
-            KT gkey;
-            unsigned gpos_u;
-            int gw;
             {
-                const KT k = lane < C ? (KT)s_cand[lane][0] : (KT)0;
-                const unsigned p = lane < C ? (unsigned)s_cand[lane][1] : PB_NOPOS;
+                const KT k = lane < C ? (KT)s_cand[0][lane][0] : (KT)0;
+                const unsigned p = lane < C ? (unsigned)s_cand[0][lane][1] : PB_NOPOS;
                 warp_argmax<KT>(k, p, gkey, gpos_u, gw);
+            }
+            urow = s_rows + gw * W;
+            if (warp == NW - 1) s_piv[c * W + lane] = urow[lane];  // keep the pivot row for the block update
+            recip_w = s_recip[gw];
             }
             const int gpos = (int)gpos_u;
             const bool sing = (gkey == 0);
-            const T* urow = s_rows + gw * W;
             if (rank == 0 && tid == 0) {
                 ipiv[j] = row_base + gpos;
                 if (sing) *info = step_base + j;  // last zero-pivot step wins (getrf.rs:72-73)
             }
-            if (warp == NW - 1) s_piv[c * W + lane] = urow[lane];  // keep the pivot row for the block update
             PB_STAMP(4);
-            const T recip = sing ? T(0) : s_recip[gw];
+            const T recip = sing ? T(0) : recip_w;
             T u[SW];  // u[k] = pivot-row entry of column j+k (zero beyond the sub-panel)
 #pragma unroll
             for (int k = 1; k < SW; ++k) u[k] = (k < left) ? urow[j + k] : T(0);
@@ -371,10 +443,10 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
 #undef PB_STAMP
 }
 
-template <class T, int RPT>
+template <class T, int RPT, bool ASYNC>
 int launch_blocked(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info,
                    int32_t step_base, cudaStream_t s) {
-    auto kern = panel_blocked_kernel<T, RPT>;
+    auto kern = panel_blocked_kernel<T, RPT, ASYNC>;
     constexpr int TPB = PB_ROWS / RPT;
     const size_t smem = PBSmem<T>::total;
     static int max_cluster = -1;
@@ -428,9 +500,14 @@ template <class T>
 int panel_blocked_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info,
                       int32_t step_base, cudaStream_t s) {
     if (w > PB_W || rows > (int64_t)PB_MAXC * PB_ROWS) return LAIR_B200_ERR_UNSUPPORTED;
-    if (ctx().opt.panel_rpt == 1) return launch_blocked<T, 1>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
-    if (ctx().opt.panel_rpt == 4) return launch_blocked<T, 4>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
-    return launch_blocked<T, 2>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+    const bool async = ctx().opt.panel_exchange != 0;
+#define PB_GO(RPT)                                                                                                        \
+    return async ? launch_blocked<T, RPT, true>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)                \
+                 : launch_blocked<T, RPT, false>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)
+    if (ctx().opt.panel_rpt == 1) PB_GO(1);
+    if (ctx().opt.panel_rpt == 4) PB_GO(4);
+    PB_GO(2);
+#undef PB_GO
 }
 
 int panel_blocked_timing(long long* out8, bool clear) {

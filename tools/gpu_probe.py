@@ -145,13 +145,16 @@ def sec_panel():
             a = a0.clone()
             ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
             info = torch.empty(1, dtype=torch.int32, device="cuda")
-            for cl, grp, rpt in ((2, 4, 1), (2, 4, 2), (2, 4, 4), (1, 4, 2), (0, 4, 2)):
+            for cl, grp, rpt, exch in ((2, 4, 1, 1), (2, 4, 2, 1), (2, 4, 4, 1), (2, 4, 2, 0), (1, 4, 2, 0), (0, 4, 2, 0)):
                 _ffi.set_option("panel_cluster", cl)
                 _ffi.set_option("panel_group", grp)
                 _ffi.set_option("panel_rpt", rpt)
+                _ffi.set_option("panel_exchange", exch)
                 best, med = timeit(lambda: _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
                                    setup=lambda: a.copy_(a0))
-                out(bench=f"{pfx}panel", cluster=cl, group=grp, rpt=rpt, m=m, w=w, ms_best=best, ms_med=med, us_per_column=best * 1e3 / w)
+                out(bench=f"{pfx}panel", cluster=cl, group=grp, rpt=rpt, exchange=exch, m=m, w=w, ms_best=best, ms_med=med,
+                    us_per_column=best * 1e3 / w, piv_sum=int(ipiv.sum()), checksum=float(a.double().sum()))
+            _ffi.set_option("panel_exchange", 1)
             _ffi.set_option("panel_cluster", 2)
             _ffi.set_option("panel_group", 4)
             _ffi.set_option("panel_rpt", 2)
@@ -162,12 +165,13 @@ def sec_paneltiming():
     buf = (ctypes.c_longlong * 8)()
     for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
         fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
-        for m in (1024, 8192):
+        for m, exch in ((1024, 1), (8192, 1), (8192, 0)):
             w = 32
             a0 = torch.rand(m, w, dtype=dt, device="cuda")
             a = a0.clone()
             ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
             info = torch.empty(1, dtype=torch.int32, device="cuda")
+            _ffi.set_option("panel_exchange", exch)
             _ffi.set_option("panel_timing", 1)
             _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream()))
             torch.cuda.synchronize()
@@ -180,7 +184,7 @@ def sec_paneltiming():
             _ffi.set_option("panel_timing", 0)
             cols = max(1, buf[6])
             names = ["candidate", "syncthreads", "cta_cand_push", "cluster_sync", "winner", "update"]
-            out(bench=f"{pfx}panel_phases", kernel=_ffi.get_option("panel_cluster"), rpt=_ffi.get_option("panel_rpt"), m=m,
+            out(bench=f"{pfx}panel_phases", kernel=_ffi.get_option("panel_cluster"), rpt=_ffi.get_option("panel_rpt"), exchange=exch, m=m,
                 columns=int(buf[6]), cycles_per_column={n: buf[i] / cols for i, n in enumerate(names)},
                 kernel_cycles_per_launch=buf[7] / 3)
             # fixed vs per-column cost: whole-call time for narrower panels
@@ -189,7 +193,8 @@ def sec_paneltiming():
                 aw = aw0.clone()
                 best, med = timeit(lambda: _ffi.check(fn(m, ww, aw.data_ptr(), ww, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
                                    setup=lambda: aw.copy_(aw0))
-                out(bench=f"{pfx}panel_width", m=m, w=ww, us_total=best * 1e3)
+                out(bench=f"{pfx}panel_width", m=m, w=ww, exchange=exch, us_total=best * 1e3)
+            _ffi.set_option("panel_exchange", 1)
 
 
 def sec_getrf():

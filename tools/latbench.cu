@@ -121,6 +121,62 @@ __global__ void k_cluster_push(long long* cyc, unsigned* out) {
     out[threadIdx.x] = (unsigned)acc;
     if (threadIdx.x == 0 && rank == 0) cyc[0] = (t1 - t0);
 }
+// st.async push of NV2 x 16 B to every peer, completion through the receiver's mbarrier (no
+// cluster barrier): the candidate exchange of a panel column without cluster.sync
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+template <int NV2>
+__global__ void k_cluster_stasync(long long* cyc, unsigned* out) {
+    cg::cluster_group cl = cg::this_cluster();
+    __shared__ __align__(16) unsigned long long slots[2][16][2 * NV2];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const unsigned C = cl.num_blocks(), rank = cl.block_rank();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cl.sync();
+    unsigned long long acc = threadIdx.x;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+        const int b = i & 1;
+        const unsigned bar = smem_u32(&mbar[b]);
+        if (threadIdx.x == 0) {
+            unsigned long long st;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(st) : "r"(bar), "r"(C * NV2 * 16u) : "memory");
+        }
+        for (unsigned idx = threadIdx.x; idx < C * NV2; idx += blockDim.x) {
+            const unsigned peer = idx % C, chunk = idx / C;
+            const unsigned raddr = mapa_u32(smem_u32(&slots[b][rank][2 * chunk]), peer);
+            const unsigned rbar = mapa_u32(bar, peer);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+                         "l"(acc + i), "l"(acc), "r"(rbar)
+                         : "memory");
+        }
+        const unsigned parity = (i >> 1) & 1;
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        }
+        acc += slots[b][(rank + 1) % C][threadIdx.x % (2 * NV2)];
+        __syncthreads();
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = (unsigned)acc;
+    if (threadIdx.x == 0 && rank == 0) cyc[0] = (t1 - t0);
+    cl.sync();
+}
 // remote load latency (pointer chase through a peer's shared memory)
 __global__ void k_dsmem_load(long long* cyc, unsigned* out) {
     cg::cluster_group cl = cg::this_cluster();
@@ -188,6 +244,12 @@ int main() {
         run(nm, [&] { launch_cluster(k_cluster_sync, cs, 512, cyc); }, cyc);
         snprintf(nm, sizeof nm, "cluster_push256B_sync_read_c%d_t128", cs);
         run(nm, [&] { launch_cluster(k_cluster_push, cs, 128, cyc, (unsigned*)out); }, cyc);
+        snprintf(nm, sizeof nm, "stasync_push16B_mbar_wait_c%d_t128", cs);
+        run(nm, [&] { launch_cluster(k_cluster_stasync<1>, cs, 128, cyc, (unsigned*)out); }, cyc);
+        snprintf(nm, sizeof nm, "stasync_push16B_mbar_wait_c%d_t512", cs);
+        run(nm, [&] { launch_cluster(k_cluster_stasync<1>, cs, 512, cyc, (unsigned*)out); }, cyc);
+        snprintf(nm, sizeof nm, "stasync_push272B_mbar_wait_c%d_t512", cs);
+        run(nm, [&] { launch_cluster(k_cluster_stasync<17>, cs, 512, cyc, (unsigned*)out); }, cyc);
         snprintf(nm, sizeof nm, "dsmem_load_chase_c%d", cs);
         run(nm, [&] { launch_cluster(k_dsmem_load, cs, 32, cyc, (unsigned*)out); }, cyc);
     }
