@@ -138,6 +138,7 @@ struct Options {
     int64_t panel_rpt = 2;      // rows per thread of the blocked cluster panel kernel (1, 2, 4)
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
+    int64_t panel_w64 = 1;      // panel_blocked: take a whole 64-column block in one launch when its rows fit
     int64_t panel_exchange = 1; // panel_blocked: 1 = st.async record push + winner-row pull, 0 = cluster barrier + pull
     int64_t fuse_swap_trsm = 1; // block steps of width <= 64: one fused laswp+trsm launch (laswp_trsm.cu)
     int64_t trsm_dataflow = 1;  // f64 getrs: persistent dataflow triangular solves (trsm_dataflow.cu)
@@ -194,6 +195,7 @@ template <class T> int getrf_batched32x2_dev(int64_t batch, T* d_a, int32_t* d_i
 template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r0, int64_t c0, int64_t w, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
 // in-kernel blocked cluster panel (panel_blocked.cu): 8-column register sub-panels, RPT rows per thread
 template <class T> int panel_blocked_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
+template <class T> int panel_blocked_max_width(int64_t rows);
 int panel_blocked_timing(long long* out8, bool clear);
 // X = T^-1 B in place, T = unit-lower / upper triangle of d_lu (trsm_dataflow.cu)
 int dtrsm_dataflow_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);

@@ -185,6 +185,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.fuse_swap_trsm = value;
     } else if (!strcmp(name, "panel_exchange")) {
         o.panel_exchange = value;
+    } else if (!strcmp(name, "panel_w64")) {
+        o.panel_w64 = value;
     } else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;
@@ -207,6 +209,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "trsm_dataflow")) *value = o.trsm_dataflow;
     else if (!strcmp(name, "fuse_swap_trsm")) *value = o.fuse_swap_trsm;
     else if (!strcmp(name, "panel_exchange")) *value = o.panel_exchange;
+    else if (!strcmp(name, "panel_w64")) *value = o.panel_w64;
     else {
         set_error("unknown option '%s'", name);
         return LAIR_B200_ERR_INVALID;

@@ -35,22 +35,23 @@ namespace cg = cooperative_groups;
 namespace lair {
 namespace {
 
-constexpr int PB_W = 32;       // panel width handled by one launch
+constexpr int PB_W = 32;       // default panel width handled by one launch (a 64-wide variant exists)
 constexpr int PB_SW = 8;       // sub-panel width (register resident)
-constexpr int PB_ROWS = 512;   // rows per CTA
+constexpr int PB_ROWS32 = 512; // rows per CTA, 32-wide panels
+template <class T> constexpr int pb_rows64() { return sizeof(T) == 8 ? 256 : 512; }  // rows per CTA, 64-wide panels
 constexpr int PB_MAXC = 16;    // CTAs per cluster
 constexpr unsigned PB_NOPOS = 0x7fffffffu;
 
 __device__ long long g_pb_timing[8];
 
-template <class T>
+template <class T, int W, int ROWS>
 struct PBSmem {
     static constexpr int VEC = 16 / sizeof(T);
-    static constexpr int LD = PB_W + VEC;  // row pitch: 16-byte aligned rows, conflict-free 128-bit row access
-    static constexpr size_t panel_bytes = (size_t)PB_ROWS * LD * sizeof(T);          // the CTA's rows
-    static constexpr size_t rows_bytes = (size_t)PB_MAXC * PB_W * sizeof(T);         // pulled candidate rows
-    static constexpr size_t mine_bytes = (size_t)2 * PB_W * sizeof(T);               // published candidate row (2 parities)
-    static constexpr size_t piv_bytes = (size_t)PB_SW * PB_W * sizeof(T);            // the sub-panel's pivot rows
+    static constexpr int LD = W + VEC;  // row pitch: 16-byte aligned rows, conflict-free 128-bit row access
+    static constexpr size_t panel_bytes = (size_t)ROWS * LD * sizeof(T);           // the CTA's rows
+    static constexpr size_t rows_bytes = (size_t)PB_MAXC * W * sizeof(T);          // pulled candidate rows
+    static constexpr size_t mine_bytes = (size_t)2 * W * sizeof(T);                // published candidate row (2 parities)
+    static constexpr size_t piv_bytes = (size_t)PB_SW * W * sizeof(T);             // the sub-panel's pivot rows
     static constexpr size_t total = panel_bytes + rows_bytes + mine_bytes + piv_bytes + 64;
 };
 
@@ -80,20 +81,23 @@ __device__ __forceinline__ void pb_mbar_wait_cluster(unsigned bar, unsigned pari
 //                (completion counted by the receiver's mbarrier: no cluster barrier in the column
 //                loop; 448 vs ~1900 cycles for 16 CTAs, profiles/r1_latbench_b200.jsonl), each warp
 //                then decides the winner from its own shared memory and pulls only the winner's row.
-template <class T, int RPT, bool ASYNC>
+// W x PB_ROWS_ per CTA: 32 x 512 (any exchange) or 64 x 256 (f64) / 64 x 512 (f32), ASYNC only: a
+// whole 64-column block of the outer sweep in ONE launch when its rows fit 16 CTAs.
+template <class T, int RPT, bool ASYNC, int W, int PB_ROWS>
 __global__ void __launch_bounds__(PB_ROWS / RPT, 1)
 panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __restrict__ ipiv, int row_base,
                      int32_t* __restrict__ info, int step_base, int timing) {
     using K = PivotKey<T>;
     using KT = typename K::type;
-    using SM = PBSmem<T>;
+    using SM = PBSmem<T, W, PB_ROWS>;
     constexpr int TPB = PB_ROWS / RPT;
     constexpr int NW = TPB / 32;
     constexpr int VEC = SM::VEC;
     constexpr int LD = SM::LD;
-    constexpr int W = PB_W, SW = PB_SW;
+    constexpr int SW = PB_SW;
+    constexpr int WL = W / 32;  // panel columns per lane in the row copies
     struct alignas(16) V16 { T v[VEC]; };
-    static_assert(W == 32, "one lane per panel column in the row copies");
+    static_assert(W == 32 || (W == 64 && ASYNC), "64-wide panels use the st.async exchange");
 
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
@@ -240,7 +244,9 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 int cw;
                 warp_argmax<KT>(k, p, ckey, cpos, cw);
                 const int lrow = s_wrow[cw < NW ? cw : 0];
-                s_mine[parity * W + lane] = s_panel[lrow * LD + lane];  // garbage when the CTA has no live row: never selected
+#pragma unroll
+                for (int q = 0; q < WL; ++q)  // garbage when the CTA has no live row: never selected
+                    s_mine[parity * W + lane + 32 * q] = s_panel[lrow * LD + lane + 32 * q];
                 if constexpr (ASYNC) {
                     const unsigned bar = pb_smem_u32(&s_mbar[parity]);
                     if (lane == 0) {  // arm this column's phase: C records of 16 bytes will land here
@@ -275,9 +281,15 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                     const KT k = lane < C ? (KT)s_cand[parity][lane][0] : (KT)0;
                     const unsigned p = lane < C ? (unsigned)s_cand[parity][lane][1] : PB_NOPOS;
                     warp_argmax<KT>(k, p, gkey, gpos_u, gw);
-                    const T v = cluster.map_shared_rank(s_mine + parity * W, gw < C ? gw : rank)[lane];
-                    s_rows[lane] = v;
-                    s_piv[c * W + lane] = v;  // keep the pivot row for the block update
+                    const T* remote = cluster.map_shared_rank(s_mine + parity * W, gw < C ? gw : rank);
+                    T v[WL];
+#pragma unroll
+                    for (int q = 0; q < WL; ++q) v[q] = remote[lane + 32 * q];
+#pragma unroll
+                    for (int q = 0; q < WL; ++q) {
+                        s_rows[lane + 32 * q] = v[q];
+                        s_piv[c * W + lane + 32 * q] = v[q];  // keep the pivot row for the block update
+                    }
                     if (lane == 0) {
                         s_win[0] = (unsigned long long)gkey;
                         s_win[1] = (unsigned long long)gpos_u;
@@ -443,12 +455,12 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
 #undef PB_STAMP
 }
 
-template <class T, int RPT, bool ASYNC>
+template <class T, int RPT, bool ASYNC, int W, int ROWS>
 int launch_blocked(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info,
                    int32_t step_base, cudaStream_t s) {
-    auto kern = panel_blocked_kernel<T, RPT, ASYNC>;
-    constexpr int TPB = PB_ROWS / RPT;
-    const size_t smem = PBSmem<T>::total;
+    auto kern = panel_blocked_kernel<T, RPT, ASYNC, W, ROWS>;
+    constexpr int TPB = ROWS / RPT;
+    const size_t smem = PBSmem<T, W, ROWS>::total;
     static int max_cluster = -1;
     if (max_cluster < 0) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -470,7 +482,7 @@ int launch_blocked(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv
         }
         (void)cudaGetLastError();
     }
-    int need = (int)((rows + PB_ROWS - 1) / PB_ROWS);
+    int need = (int)((rows + ROWS - 1) / ROWS);
     int csize = 1;
     while (csize < need) csize *= 2;
     if (csize > max_cluster) return LAIR_B200_ERR_UNSUPPORTED;
@@ -495,15 +507,28 @@ int launch_blocked(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv
 
 }  // namespace
 
+// Widest panel one launch of this kernel takes for `rows` rows: 64 (option panel_w64, st.async
+// exchange) while the rows fit 16 CTAs of the 64-wide layout, else 32, else 0.
+template <class T>
+int panel_blocked_max_width(int64_t rows) {
+    if (ctx().opt.panel_w64 != 0 && ctx().opt.panel_exchange != 0 && rows <= (int64_t)PB_MAXC * pb_rows64<T>()) return 64;
+    if (rows <= (int64_t)PB_MAXC * PB_ROWS32) return 32;
+    return 0;
+}
+
 // Returns LAIR_B200_ERR_UNSUPPORTED (without setting an error) when the panel does not fit one cluster.
 template <class T>
 int panel_blocked_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info,
                       int32_t step_base, cudaStream_t s) {
-    if (w > PB_W || rows > (int64_t)PB_MAXC * PB_ROWS) return LAIR_B200_ERR_UNSUPPORTED;
+    if (w > 32) {
+        if (w > panel_blocked_max_width<T>(rows)) return LAIR_B200_ERR_UNSUPPORTED;
+        return launch_blocked<T, 2, true, 64, pb_rows64<T>()>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+    }
+    if (rows > (int64_t)PB_MAXC * PB_ROWS32) return LAIR_B200_ERR_UNSUPPORTED;
     const bool async = ctx().opt.panel_exchange != 0;
-#define PB_GO(RPT)                                                                                                        \
-    return async ? launch_blocked<T, RPT, true>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)                \
-                 : launch_blocked<T, RPT, false>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)
+#define PB_GO(RPT)                                                                                                           \
+    return async ? launch_blocked<T, RPT, true, 32, PB_ROWS32>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)    \
+                 : launch_blocked<T, RPT, false, 32, PB_ROWS32>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)
     if (ctx().opt.panel_rpt == 1) PB_GO(1);
     if (ctx().opt.panel_rpt == 4) PB_GO(4);
     PB_GO(2);
@@ -522,5 +547,7 @@ int panel_blocked_timing(long long* out8, bool clear) {
 
 template int panel_blocked_dev<float>(int64_t, int64_t, float*, int64_t, int32_t*, int32_t, int32_t*, int32_t, cudaStream_t);
 template int panel_blocked_dev<double>(int64_t, int64_t, double*, int64_t, int32_t*, int32_t, int32_t*, int32_t, cudaStream_t);
+template int panel_blocked_max_width<float>(int64_t);
+template int panel_blocked_max_width<double>(int64_t);
 
 }  // namespace lair

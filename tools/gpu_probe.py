@@ -160,6 +160,25 @@ def sec_panel():
             _ffi.set_option("panel_rpt", 2)
 
 
+def sec_panel64():
+    """One 64-column block: a single 64-wide panel launch vs two 32-wide panels + in-block update."""
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for m in (1024, 2048, 4096, 8192):
+            w = 64
+            a0 = torch.rand(m, w, dtype=dt, device="cuda")
+            a = a0.clone()
+            ipiv = torch.empty(w, dtype=torch.int32, device="cuda")
+            info = torch.empty(1, dtype=torch.int32, device="cuda")
+            for w64 in (0, 1):
+                _ffi.set_option("panel_w64", w64)
+                best, med = timeit(lambda: _ffi.check(fn(m, w, a.data_ptr(), w, ipiv.data_ptr(), info.data_ptr(), stream())), reps=5,
+                                   setup=lambda: a.copy_(a0))
+                out(bench=f"{pfx}block64", panel_w64=w64, m=m, w=w, us_best=best * 1e3, us_med=med * 1e3, piv_sum=int(ipiv.sum()),
+                    checksum=float(a.double().sum()))
+            _ffi.set_option("panel_w64", 1)
+
+
 def sec_paneltiming():
     """Per-phase SM-cycle breakdown of the cluster panel kernel (debug counters)."""
     buf = (ctypes.c_longlong * 8)()
