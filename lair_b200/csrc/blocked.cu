@@ -86,20 +86,26 @@ struct Factor {
         // outer block width: with lookahead the factorization is bound by the panel path up to
         // n ~ 8192 (narrow blocks keep it short) and by the trailing GEMM beyond (wide blocks feed
         // the DMMA kernel with a deeper K); measured on B200, profiles/r1_bench_history.md
-        int64_t nb = ctx().opt.nb;
-        if (nb <= 0) nb = kmin <= 10240 ? 64 : (kmin <= 14336 ? 128 : 256);
-        const bool look = ctx().opt.lookahead != 0 && kmin > nb;
+        // The width follows the REMAINING size: while the trailing matrix is large the sweep is bound by
+        // the GEMM on stream M (wide blocks = deeper K), once it is small by the panel chain on P.
+        const int64_t fixed_nb = ctx().opt.nb, t1 = ctx().opt.nb_t1, t2 = ctx().opt.nb_t2;
+        auto pick = [&](int64_t j) {
+            const int64_t rem = kmin - j;
+            const int64_t v = fixed_nb > 0 ? fixed_nb : (rem > t2 ? 256 : (rem > t1 ? 128 : 64));
+            return v < rem ? v : rem;
+        };
+        const bool look = ctx().opt.lookahead != 0 && kmin > pick(0);
         cudaStream_t M = s, P = look ? ctx().aux_stream : s;
         cudaEvent_t EP = ctx().ev[0], EN = ctx().ev[1];
         if (look) {
             LAIR_CUDA_CHECK(cudaEventRecord(EN, M));  // P starts after everything already queued on the caller's stream
             LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
         }
-        LAIR_CHECK(rec(0, kmin < nb ? kmin : nb, P));
-        for (int64_t j0 = 0; j0 < kmin; j0 += nb) {
-            const int64_t jb = (kmin - j0) < nb ? (kmin - j0) : nb;
+        int64_t jb = pick(0);
+        LAIR_CHECK(rec(0, jb, P));
+        for (int64_t j0 = 0; j0 < kmin; j0 += jb, jb = pick(j0)) {
             const int64_t c0 = j0 + jb;                      // first column right of the block
-            const int64_t nb2 = (c0 < kmin) ? ((kmin - c0) < nb ? (kmin - c0) : nb) : 0;  // width of the next block to factor
+            const int64_t nb2 = (c0 < kmin) ? pick(c0) : 0;  // width of the next block to factor
             if (look) {
                 LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
                 LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));

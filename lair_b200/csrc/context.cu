@@ -163,6 +163,10 @@ int lair_b200_set_option(const char* name, int64_t value) {
             return LAIR_B200_ERR_INVALID;
         }
         o.nb = value;
+    } else if (!strcmp(name, "nb_t1")) {
+        o.nb_t1 = value;
+    } else if (!strcmp(name, "nb_t2")) {
+        o.nb_t2 = value;
     } else if (!strcmp(name, "small_n")) {
         o.small_n = value;
     } else if (!strcmp(name, "lookahead")) {
@@ -198,6 +202,8 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     if (!name || !value) return LAIR_B200_ERR_INVALID;
     const Options& o = g_ctx.opt;
     if (!strcmp(name, "nb")) *value = o.nb;
+    else if (!strcmp(name, "nb_t1")) *value = o.nb_t1;
+    else if (!strcmp(name, "nb_t2")) *value = o.nb_t2;
     else if (!strcmp(name, "small_n")) *value = o.small_n;
     else if (!strcmp(name, "lookahead")) *value = o.lookahead;
     else if (!strcmp(name, "batched_cfg")) *value = o.batched_cfg;

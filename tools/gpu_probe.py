@@ -160,6 +160,30 @@ def sec_panel():
             _ffi.set_option("panel_rpt", 2)
 
 
+def sec_nbsched():
+    """Block-width schedule: sweep the remaining-size thresholds of the automatic nb."""
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for n in (4096, 8192, 12288, 16384):
+            if pfx == "s" and n > 8192:
+                continue
+            a0 = torch.rand(n, n, dtype=dt, device="cuda") * 10
+            a = a0.clone()
+            ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+            info = torch.empty(1, dtype=torch.int32, device="cuda")
+            for t1, t2 in ((1 << 30, 1 << 30), (8192, 1 << 30), (6144, 1 << 30), (5120, 1 << 30), (4096, 1 << 30), (3072, 1 << 30),
+                           (6144, 14336), (6144, 12288), (6144, 10240), (4096, 10240), (0, 1 << 30), (0, 0)):
+                if n <= 8192 and t2 < (1 << 30) and t2 >= n:
+                    continue
+                _ffi.set_option("nb_t1", t1)
+                _ffi.set_option("nb_t2", t2)
+                best, med = timeit(lambda: _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream())),
+                                   reps=3, warm=1, setup=lambda: a.copy_(a0))
+                out(bench=f"{pfx}getrf_nbsched", n=n, t1=t1, t2=t2, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9)
+    _ffi.set_option("nb_t1", 5120)
+    _ffi.set_option("nb_t2", 10240)
+
+
 def sec_panel64():
     """One 64-column block: a single 64-wide panel launch vs two 32-wide panels + in-block update."""
     for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
