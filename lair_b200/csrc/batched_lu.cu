@@ -237,6 +237,7 @@ int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t
     int64_t cfg = ctx().opt.batched_cfg;
     if (cfg < 0) cfg = sizeof(T) == 8 ? 5 : 0;  // measured best on B200: f64 130.7 M/s (cfg 5), f32 239.6 M/s (cfg 0)
     if (!full) return launch_batched<T, 4, kLo, false, 0>(batch, (int)n, d_a, d_ipiv, d_info, s);
+    if (cfg & 16) return getrf_batched32v3_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // one warp per CTA, branch-free
     if (cfg & 8) return getrf_batched32x2_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // two matrices per warp
     switch (cfg & 7) {
         case 1: return launch_batched<T, 4, kHi, true, 0>(batch, 32, d_a, d_ipiv, d_info, s);

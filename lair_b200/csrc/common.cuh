@@ -193,6 +193,10 @@ int panel_cluster_timing(long long* out8, bool clear);
 template <class T> int laswp_trsm_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k, const int32_t* d_ipiv, const T* d_l, int64_t ldl, cudaStream_t s);
 // 32x32 batched LU, two matrices per warp (batched_lu2.cu)
 template <class T> int getrf_batched32x2_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+// one warp per CTA, branch-free column step, packed f32x2 updates (batched_lu3.cu)
+template <class T> int getrf_batched32v3_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v3_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v3_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // factor one block column stored at local columns [c0, c0+w), diagonal at row r0 (blocked.cu)
 template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r0, int64_t c0, int64_t w, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
 // in-kernel blocked cluster panel (panel_blocked.cu): 8-column register sub-panels, RPT rows per thread

@@ -43,10 +43,11 @@ def test_batched32_bit_exact(lair, dt, dist):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17])
 def test_batched32_every_variant_bit_exact(lair, dt, cfg):
-    """Every tuning variant of the batched kernel (incl. two matrices per warp, odd batch, ties,
-    singular and NaN inputs) is bit-identical to the oracle."""
+    """Every tuning variant of the batched kernel (incl. two matrices per warp, one warp per CTA
+    with packed f32x2 updates, odd batch, ties, singular, NaN, infinite and subnormal inputs) is
+    bit-identical to the oracle."""
     from lair_b200 import _ffi
     rng = np.random.default_rng(100 + cfg)
     a0 = _rand(rng, (1001, 32, 32), dt)
@@ -54,6 +55,9 @@ def test_batched32_every_variant_bit_exact(lair, dt, cfg):
     a0[6] = 0
     a0[7, :, 3] = 0
     a0[8, 4, 4] = np.nan
+    a0[9, 2, 2] = np.inf
+    a0[10] = a0[10] * dt(1e-39 if dt == np.float32 else 1e-309)  # subnormal pivots: reciprocals overflow
+    a0[11] = a0[11] * dt(1e37 if dt == np.float32 else 1e307)    # huge entries: subnormal reciprocals
     a0[1000] = 1
     ref = a0.copy()
     piv_o, info_o = oracle.getrf_batched(ref)

@@ -127,13 +127,29 @@ def sec_batched():
         a = a0.clone()
         ipiv = torch.empty(batch, 32, dtype=torch.int32, device="cuda")
         info = torch.empty(batch, dtype=torch.int32, device="cuda")
-        for cfg in (0, 1, 4, 5, 8, 9):
+        for cfg in (0, 1, 4, 5, 16, 17):
             _ffi.set_option("batched_cfg", cfg)
             best, med = timeit(lambda: _ffi.check(fn(batch, 32, a.data_ptr(), ipiv.data_ptr(), info.data_ptr(), stream())),
                                reps=5, setup=lambda: a.copy_(a0))
             out(bench=f"{pfx}getrf_batched32", cfg=cfg, batch=batch, ms_best=best, ms_med=med, mats_per_s=batch / best * 1e3,
                 gbs=batch * bpm / best * 1e-6, frac_of_6453=batch * bpm / best * 1e-6 / 6453.7)
         _ffi.set_option("batched_cfg", -1)
+
+
+def sec_batchedone():
+    """One launch per type of the batched kernel chosen by $BATCHED_CFG (for an ncu capture)."""
+    cfg = int(os.environ.get("BATCHED_CFG", "-1"))
+    batch = 1_000_000
+    for dt, pfx in ((torch.float32, "s"), (torch.float64, "d")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_batched_dev")
+        a = torch.rand(batch, 32, 32, dtype=dt, device="cuda") * 10
+        ipiv = torch.empty(batch, 32, dtype=torch.int32, device="cuda")
+        info = torch.empty(batch, dtype=torch.int32, device="cuda")
+        _ffi.set_option("batched_cfg", cfg)
+        _ffi.check(fn(batch, 32, a.data_ptr(), ipiv.data_ptr(), info.data_ptr(), stream()))
+        torch.cuda.synchronize()
+        _ffi.set_option("batched_cfg", -1)
+        out(bench=f"{pfx}getrf_batched32_once", cfg=cfg)
 
 
 def sec_panel():
