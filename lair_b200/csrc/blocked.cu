@@ -158,8 +158,17 @@ int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const
                       cudaStream_t s) {
     LAIR_REQUIRE(n >= 0 && nrhs >= 0 && lda >= n && ldb >= nrhs, "getrs: bad shape");
     if (n == 0 || nrhs == 0) return LAIR_B200_OK;
-    LAIR_CHECK(laswp_dev<T>(nrhs, d_b, ldb, 0, n, d_ipiv, s));
+    // b <- P b (getrs.rs:22): all n interchanges on a tall narrow matrix collapse into one permutation
+    if (ctx().opt.laswp_perm != 0 && n >= 512 && (double)n * (double)nrhs * sizeof(T) <= 256.0 * 1024 * 1024)
+        LAIR_CHECK(laswp_perm_dev<T>(n, nrhs, d_b, ldb, 0, n, d_ipiv, s));
+    else
+        LAIR_CHECK(laswp_dev<T>(nrhs, d_b, ldb, 0, n, d_ipiv, s));
     if constexpr (sizeof(T) == 8) {
+        if (ctx().opt.trsm_dataflow >= 2) {
+            // flag-in-data exchange + pre-inverted diagonal blocks (trsm_ll.cu)
+            LAIR_CHECK(dtrsm_ll_dev(false, n, nrhs, d_lu, lda, d_b, ldb, s));
+            return dtrsm_ll_dev(true, n, nrhs, d_lu, lda, d_b, ldb, s);
+        }
         if (ctx().opt.trsm_dataflow) {
             // one persistent dataflow kernel per triangle (trsm_dataflow.cu)
             LAIR_CHECK(dtrsm_dataflow_dev(false, n, nrhs, d_lu, lda, d_b, ldb, s));

@@ -142,8 +142,11 @@ struct Options {
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
     int64_t panel_w64 = 1;      // panel_blocked: take a whole 64-column block in one launch when its rows fit
     int64_t panel_exchange = 1; // panel_blocked: 1 = st.async record push + winner-row pull, 0 = cluster barrier + pull
+    int64_t laswp_perm = 1;     // getrs: apply P to the right-hand sides as one collapsed permutation (laswp_perm.cu)
     int64_t fuse_swap_trsm = 1; // block steps of width <= 64: one fused laswp+trsm launch (laswp_trsm.cu)
-    int64_t trsm_dataflow = 1;  // f64 getrs: persistent dataflow triangular solves (trsm_dataflow.cu)
+    int64_t trsm_dataflow = 2;  // f64 getrs: 2 flag-in-data dataflow solves with pre-inverted diagonal blocks (trsm_ll.cu),
+                                // 1 flag-word dataflow solves with substitution (trsm_dataflow.cu), 0 recursive TRSM + GEMM
+    int64_t trsm_rb = 32;       // row-block height of the flag-word dataflow solves (32 or 64; same speed, measured)
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
 };
 
@@ -205,6 +208,9 @@ template <class T> int panel_blocked_max_width(int64_t rows);
 int panel_blocked_timing(long long* out8, bool clear);
 // X = T^-1 B in place, T = unit-lower / upper triangle of d_lu (trsm_dataflow.cu)
 int dtrsm_dataflow_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);
+// all interchanges ipiv[k0..k1) on rows [k0, nrows) of a tall narrow matrix, as one permutation (laswp_perm.cu)
+template <class T> int laswp_perm_dev(int64_t nrows, int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s);
+int dtrsm_ll_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);
 // 1 if a panel exchange timed out since the last clear (results are then invalid)
 int panel_error_flag(bool clear);
 

@@ -185,6 +185,10 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.panel_timing = value;
     } else if (!strcmp(name, "trsm_dataflow")) {
         o.trsm_dataflow = value;
+    } else if (!strcmp(name, "laswp_perm")) {
+        o.laswp_perm = value;
+    } else if (!strcmp(name, "trsm_rb")) {
+        o.trsm_rb = value;
     } else if (!strcmp(name, "fuse_swap_trsm")) {
         o.fuse_swap_trsm = value;
     } else if (!strcmp(name, "panel_exchange")) {
@@ -213,6 +217,8 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "panel_rpt")) *value = o.panel_rpt;
     else if (!strcmp(name, "panel_timing")) *value = o.panel_timing;
     else if (!strcmp(name, "trsm_dataflow")) *value = o.trsm_dataflow;
+    else if (!strcmp(name, "laswp_perm")) *value = o.laswp_perm;
+    else if (!strcmp(name, "trsm_rb")) *value = o.trsm_rb;
     else if (!strcmp(name, "fuse_swap_trsm")) *value = o.fuse_swap_trsm;
     else if (!strcmp(name, "panel_exchange")) *value = o.panel_exchange;
     else if (!strcmp(name, "panel_w64")) *value = o.panel_w64;

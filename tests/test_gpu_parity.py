@@ -367,7 +367,8 @@ def test_blocked_getrs_matches_oracle(lair, dt, n, nrhs):
 
 @pytest.mark.parametrize("n,nrhs", [(200, 3), (777, 5), (1000, 64), (1030, 65), (2048, 130)])
 def test_getrs_dataflow_vs_recursive(lair, n, nrhs):
-    """The persistent dataflow triangular solves and the recursive TRSM agree with the oracle."""
+    """The persistent dataflow triangular solves (flag-in-data and flag-word variants) and the
+    recursive TRSM agree with the oracle."""
     from lair_b200 import _ffi
     rng = np.random.default_rng(n * 3 + nrhs)
     a0 = _rand(rng, (n, n), np.float64)
@@ -376,13 +377,17 @@ def test_getrs_dataflow_vs_recursive(lair, n, nrhs):
     piv, _ = oracle.getrf(lu)
     xo = np.stack([oracle.getrs(lu, piv, np.ascontiguousarray(b[:, r])) for r in range(0, nrhs, max(1, nrhs // 3))], axis=1)
     try:
-        for df in (1, 0):
+        for df, rb, perm in ((2, 32, 1), (2, 32, 0), (1, 64, 1), (1, 32, 0), (0, 32, 1)):
             _ffi.set_option("trsm_dataflow", df)
+            _ffi.set_option("trsm_rb", rb)
+            _ffi.set_option("laswp_perm", perm)  # P b as one collapsed permutation vs pass-by-pass interchanges
             x = lair.lapack.getrs(lu, piv, b)
             got = x[:, ::max(1, nrhs // 3)]
-            assert np.max(np.abs(got - xo)) <= 1e-7 * np.max(np.abs(xo)), (df, np.max(np.abs(got - xo)))
+            assert np.max(np.abs(got - xo)) <= 1e-7 * np.max(np.abs(xo)), (df, rb, perm, np.max(np.abs(got - xo)))
     finally:
-        _ffi.set_option("trsm_dataflow", 1)
+        _ffi.set_option("trsm_dataflow", 2)
+        _ffi.set_option("trsm_rb", 32)
+        _ffi.set_option("laswp_perm", 1)
 
 
 def test_equation_solve_end_to_end(lair):

@@ -322,16 +322,24 @@ def sec_getrs():
         for nrhs_ in (64, 1, 256):
             b0 = torch.rand(n, nrhs_, dtype=dt, device="cuda")
             b = b0.clone()
-            for df in (1, 0):
+            for df, rb in ((2, 32), (1, 32), (0, 32)):
                 _ffi.set_option("trsm_dataflow", df)
+                _ffi.set_option("trsm_rb", rb)
                 l0 = _ffi.launch_count()
                 best, med = timeit(lambda: _ffi.check(fn(n, nrhs_, a.data_ptr(), n, ipiv.data_ptr(), b.data_ptr(), nrhs_, stream())),
                                    reps=3, warm=1, setup=lambda: b.copy_(b0))
                 launches = (_ffi.launch_count() - l0) // 4
                 res = float(torch.linalg.norm(a0 @ b - b0) / (torch.linalg.norm(a0) * torch.linalg.norm(b) * n * 2.0 ** -53))
-                out(bench=f"{pfx}getrs", dataflow=df, n=n, nrhs=nrhs_, ms_best=best, launches=launches,
-                    tflops=2 * n * n * nrhs_ / best * 1e-9, residual=res)
-            _ffi.set_option("trsm_dataflow", 1)
+                b.copy_(b0)
+                torch.cuda.synchronize()
+                _ffi.profile_begin()
+                _ffi.check(fn(n, nrhs_, a.data_ptr(), n, ipiv.data_ptr(), b.data_ptr(), nrhs_, stream()))
+                prof = _ffi.profile_end()
+                out(bench=f"{pfx}getrs", dataflow=df, rb=rb, n=n, nrhs=nrhs_, ms_best=best, launches=launches,
+                    tflops=2 * n * n * nrhs_ / best * 1e-9, residual=res,
+                    family_ms={k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]})
+            _ffi.set_option("trsm_dataflow", 2)
+            _ffi.set_option("trsm_rb", 32)
 
 
 if __name__ == "__main__":
