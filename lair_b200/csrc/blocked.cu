@@ -19,6 +19,7 @@ struct Factor {
     int32_t* ipiv;
     int32_t* info;
     cudaStream_t s;  // the caller's stream: everything is ordered after / visible on it
+    const ColumnFeed* feed = nullptr;  // columns still arriving from the host (run() only)
 
     T* at(int64_t r, int64_t c) const { return A + r * lda + c; }
 
@@ -38,6 +39,12 @@ struct Factor {
             if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
         }
         LAIR_CHECK(swap_cols(c0, c1, k0, k0 + k, st));                                            // laswp  (getrf.rs:270-277)
+        if constexpr (sizeof(T) == 8) {
+            // a tall triangle (a late column chunk catching up): one persistent dataflow solve instead
+            // of the launch-per-block recursion
+            // (main stream only: the solver's workspace is not shared with the lookahead stream)
+            if (k > 256 && st == s && ctx().opt.trsm_dataflow >= 2) return dtrsm_ll_dev(false, k, c1 - c0, at(k0, lc0), lda, at(k0, c0), lda, st);
+        }
         return trsm_lower_unit_dev<T>(k, c1 - c0, at(k0, lc0), lda, at(k0, c0), lda, st);         // trsm   (:278-283)
     }
 
@@ -97,6 +104,28 @@ struct Factor {
         const bool look = ctx().opt.lookahead != 0 && kmin > pick(0);
         cudaStream_t M = s, P = look ? ctx().aux_stream : s;
         cudaEvent_t EP = ctx().ev[0], EN = ctx().ev[1];
+        // Columns still arriving from the host (ColumnFeed): the sweep only touches columns < navail.
+        // Chunk c joins -- M waits for its copy, then one update with everything factored so far --
+        // early enough that the next two blocks always lie inside the joined range, and otherwise
+        // at a quarter of its own offset, so the copies stay ahead of the sweep without the
+        // sweep waiting for the whole matrix.
+        const bool fed = feed && feed->nchunks > 1 && feed->chunk >= 512;  // first chunk holds the first two blocks
+        int joined = fed ? 1 : 0;
+        int64_t navail = fed ? (feed->chunk < n ? feed->chunk : n) : n;
+        if (feed)  // the first chunk (or, when not sweeping chunk by chunk, every chunk) has landed
+            for (int c = 0; c < (fed ? 1 : feed->nchunks); ++c) LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, feed->ready[c], 0));
+        auto join_due = [&](int64_t c0, int64_t nb2) -> int {
+            while (fed && joined < feed->nchunks) {
+                const int64_t cs = (int64_t)joined * feed->chunk;
+                if (!(c0 >= kmin || cs < c0 + nb2 + 512 || c0 * ctx().opt.stream_join_div >= cs)) break;
+                const int64_t ce = (cs + feed->chunk) < n ? (cs + feed->chunk) : n;
+                LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, feed->ready[joined], 0));
+                LAIR_CHECK(update(0, c0, cs, ce, M));  // bring the late columns up to date with blocks [0, c0)
+                navail = ce;
+                ++joined;
+            }
+            return LAIR_B200_OK;
+        };
         if (look) {
             LAIR_CUDA_CHECK(cudaEventRecord(EN, M));  // P starts after everything already queued on the caller's stream
             LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
@@ -118,8 +147,10 @@ struct Factor {
                 }
                 LAIR_CHECK(rec(c0, nb2, P));                  // ... so its panel path can start under the rest
             }
-            LAIR_CHECK(update(j0, jb, c0 + nb2, n, M));
+            LAIR_CHECK(update(j0, jb, c0 + nb2, navail, M));
             LAIR_CHECK(swap_cols(0, j0, j0, j0 + jb, M));     // interchanges reach back into L (off the critical path)
+            LAIR_CHECK(join_due(c0, nb2));                    // late column chunks catch up with blocks [0, c0): after
+                                                              // the left interchanges, so L's rows match the pivots
         }
         if (look) {  // the caller's stream sees the last panel too (already implied, kept explicit)
             LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
@@ -132,12 +163,13 @@ struct Factor {
 }  // namespace
 
 template <class T>
-int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s) {
+int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s,
+                      const ColumnFeed* feed) {
     LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf: bad shape m=%lld n=%lld lda=%lld", (long long)m, (long long)n,
                  (long long)lda);
     LAIR_REQUIRE(m < (1ll << 31) && n < (1ll << 31), "getrf: dimension too large");
     if (m == 0 || n == 0) return LAIR_B200_OK;
-    Factor<T> f{d_a, lda, m, n, d_ipiv, d_info, s};
+    Factor<T> f{d_a, lda, m, n, d_ipiv, d_info, s, feed};
     return f.run();
 }
 
@@ -180,7 +212,7 @@ int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const
 }
 
 #define INST(T)                                                                                          \
-    template int getrf_blocked_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, cudaStream_t);   \
+    template int getrf_blocked_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, cudaStream_t, const ColumnFeed*); \
     template int getrs_blocked_dev<T>(int64_t, int64_t, const T*, int64_t, const int32_t*, T*, int64_t, cudaStream_t);
 INST(float)
 INST(double)

@@ -21,10 +21,10 @@ static bool fits_small(int64_t m, int64_t n) {
 
 template <class T>
 int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout,
-              cudaStream_t s) {
+              cudaStream_t s, const ColumnFeed* feed) {
     if (fits_small<T>(m, n)) return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
     if constexpr (IsReal<T>::value) {
-        return getrf_blocked_dev<T>(m, n, d_a, lda, d_ipiv, d_info, s);
+        return getrf_blocked_dev<T>(m, n, d_a, lda, d_ipiv, d_info, s, feed);
     } else {
         // complex beyond the single-CTA limit: correct-first in-place path
         return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
@@ -45,6 +45,32 @@ static int64_t device_ld(int64_t n) {
     return (n + 31) / 32 * 32;
 }
 
+// ---- chunked upload: the factorization starts when the first column chunk has landed ---------
+// Returns true (and fills `feed`) when the matrix was queued on the copy stream in column chunks;
+// false when the caller should upload it in one piece (small, complex, or not row-contiguous).
+template <class T>
+static int upload_matrix_chunked(const T* a, int64_t m, int64_t n, int64_t rs, int64_t cs, T* d, int64_t ld, ColumnFeed* feed,
+                                 bool* chunked) {
+    *chunked = false;
+    const int64_t w = ctx().opt.stream_cols;
+    if (!IsReal<T>::value || w < 512 || fits_small<T>(m, n) || cs != 1 || rs < n || n < 2 * w || m < n / 2) return LAIR_B200_OK;
+    const int nchunks = (int)((n + w - 1) / w);
+    if (nchunks > Context::kMaxChunks) return LAIR_B200_OK;
+    Context& c = ctx();
+    for (int i = 0; i < nchunks; ++i) {
+        if (!c.chunk_ev[i]) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&c.chunk_ev[i], cudaEventDisableTiming));
+        const int64_t c0 = (int64_t)i * w, cw = (c0 + w <= n) ? w : (n - c0);
+        LAIR_CUDA_CHECK(cudaMemcpy2DAsync(d + c0, (size_t)ld * sizeof(T), a + c0, (size_t)rs * sizeof(T), (size_t)cw * sizeof(T),
+                                          (size_t)m, cudaMemcpyHostToDevice, c.copy_stream));
+        LAIR_CUDA_CHECK(cudaEventRecord(c.chunk_ev[i], c.copy_stream));
+    }
+    feed->chunk = w;
+    feed->nchunks = nchunks;
+    feed->ready = c.chunk_ev;
+    *chunked = true;
+    return LAIR_B200_OK;
+}
+
 // ---- host-pointer getrf --------------------------------------------------------------------
 template <class T>
 static int getrf_host(int64_t m, int64_t n, T* a, int64_t rs, int64_t cs, int64_t* ipiv, int64_t* info) {
@@ -63,8 +89,11 @@ static int getrf_host(int64_t m, int64_t n, T* a, int64_t rs, int64_t cs, int64_
     LAIR_CHECK(pool().get(DevicePool::kMatrix, (size_t)m * ld * sizeof(T), &dA));
     LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)k * sizeof(int32_t), &dP));
     LAIR_CHECK(pool().get(DevicePool::kInfo, sizeof(int32_t), &dI));
-    LAIR_CHECK(upload_matrix<T>(a, m, n, rs, cs, (T*)dA, ld, DevicePool::kTmpA, s));
-    LAIR_CHECK(getrf_dev<T>(m, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s));
+    ColumnFeed feed;
+    bool chunked = false;
+    LAIR_CHECK(upload_matrix_chunked<T>(a, m, n, rs, cs, (T*)dA, ld, &feed, &chunked));
+    if (!chunked) LAIR_CHECK(upload_matrix<T>(a, m, n, rs, cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CHECK(getrf_dev<T>(m, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s, chunked ? &feed : nullptr));
     LAIR_CHECK(download_matrix<T>(a, m, n, rs, cs, (const T*)dA, ld, DevicePool::kTmpA, s));
     LAIR_CHECK(download_ipiv64(ipiv, (const int32_t*)dP, k, DevicePool::kPivots64, s));
     int32_t info32 = -1;
@@ -130,9 +159,13 @@ static int gesv_host(int64_t n, int64_t nrhs, const T* a, int64_t a_rs, int64_t 
     LAIR_CHECK(pool().get(DevicePool::kRhs, (size_t)n * ldb * sizeof(T), &dB));
     LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)n * sizeof(int32_t), &dP));
     LAIR_CHECK(pool().get(DevicePool::kInfo, sizeof(int32_t), &dI));
-    LAIR_CHECK(upload_matrix<T>(a, n, n, a_rs, a_cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    ColumnFeed feed;
+    bool chunked = false;
+    LAIR_CHECK(upload_matrix_chunked<T>(a, n, n, a_rs, a_cs, (T*)dA, ld, &feed, &chunked));
+    if (!chunked) LAIR_CHECK(upload_matrix<T>(a, n, n, a_rs, a_cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CHECK(getrf_dev<T>(n, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s, chunked ? &feed : nullptr));
+    // the right-hand sides travel behind the matrix chunks: they are not needed before the solve
     LAIR_CHECK(upload_matrix<T>(b, n, nrhs, b_rs, b_cs, (T*)dB, ldb, DevicePool::kTmpB, s));
-    LAIR_CHECK(getrf_dev<T>(n, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s));
     int32_t info32 = -1;
     LAIR_CUDA_CHECK(cudaMemcpyAsync(&info32, dI, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -167,7 +200,7 @@ static int getrf_batched_host(int64_t batch, int64_t n, T* a, int32_t* ipiv, int
 }
 
 #define INST_DISPATCH(T)                                                                                         \
-    template int getrf_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t);           \
+    template int getrf_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t, const ColumnFeed*); \
     template int getrs_dev<T>(int64_t, int64_t, const T*, int64_t, const int32_t*, T*, int64_t, cudaStream_t);
 INST_DISPATCH(float)
 INST_DISPATCH(double)

@@ -142,7 +142,10 @@ struct Options {
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
     int64_t panel_w64 = 1;      // panel_blocked: take a whole 64-column block in one launch when its rows fit
     int64_t panel_exchange = 1; // panel_blocked: 1 = st.async record push + winner-row pull, 0 = cluster barrier + pull
-    int64_t laswp_perm = 1;     // getrs: apply P to the right-hand sides as one collapsed permutation (laswp_perm.cu)
+    int64_t stream_cols = 1024; // host-pointer getrf/gesv: upload the matrix in column chunks of this width and start
+                                // factoring when the first has landed (0 = upload everything first)
+    int64_t stream_join_div = 4; // a chunk starting at column cs joins the sweep once cs / stream_join_div columns are factored
+    int64_t laswp_perm = 1;    // getrs: apply P to the right-hand sides as one collapsed permutation (laswp_perm.cu)
     int64_t fuse_swap_trsm = 1; // block steps of width <= 64: one fused laswp+trsm launch (laswp_trsm.cu)
     int64_t trsm_dataflow = 2;  // f64 getrs: 2 flag-in-data dataflow solves with pre-inverted diagonal blocks (trsm_ll.cu),
                                 // 1 flag-word dataflow solves with substitution (trsm_dataflow.cu), 0 recursive TRSM + GEMM
@@ -159,6 +162,9 @@ struct Context {
     cudaStream_t stream = nullptr;        // library-owned stream for the host-pointer entry points
     cudaStream_t aux_stream = nullptr;    // second stream (lookahead / copy overlap)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;   // host -> device column chunks of the host-pointer entry points
+    static constexpr int kMaxChunks = 128;
+    cudaEvent_t chunk_ev[kMaxChunks] = {};  // chunk c of the matrix has landed (created on first use)
     // panel exchange workspace (see panel.cu)
     void* panel_ws = nullptr;
     size_t panel_ws_bytes = 0;
@@ -177,7 +183,17 @@ int ensure_scratch(size_t bytes, void** out);       // device scratch >= bytes (
 template <class T> int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
 template <class T> int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s);
 template <class T> int getrs_small_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
-template <class T> int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
+// Columns of the device matrix that are still arriving (host -> device copies on another stream)
+// while the factorization already runs: chunk c = columns [c*chunk, (c+1)*chunk), ready[c] is
+// recorded when it has landed.  The sweep restricts its trailing updates to the chunks that have
+// joined and brings a late chunk up to date with one laswp + trsm + gemm when it joins.
+struct ColumnFeed {
+    int64_t chunk = 0;
+    int nchunks = 0;
+    const cudaEvent_t* ready = nullptr;
+};
+template <class T> int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s,
+                                         const ColumnFeed* feed = nullptr);
 template <class T> int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int laswp_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s);
 template <class T> int trsm_lower_unit_dev(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* d_b, int64_t ldb, cudaStream_t s);
@@ -215,7 +231,8 @@ int dtrsm_ll_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_
 int panel_error_flag(bool clear);
 
 // ---- dispatch helpers ----------------------------------------------------------------------
-template <class T> int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s);
+template <class T> int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s,
+                                 const ColumnFeed* feed = nullptr);
 template <class T> int getrs_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 
 }  // namespace lair

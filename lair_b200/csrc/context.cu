@@ -67,6 +67,7 @@ static int init_locked(int device) {
     // the lookahead panel runs on the high-priority stream so its CTAs are placed first
     LAIR_CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.aux_stream, cudaStreamNonBlocking, hi));
     for (auto& ev : g_ctx.ev) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    LAIR_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
     if (const char* v = getenv("LAIR_B200_NB")) g_ctx.opt.nb = atoll(v);
     if (const char* v = getenv("LAIR_B200_SMALL_N")) g_ctx.opt.small_n = atoll(v);
     if (const char* v = getenv("LAIR_B200_LOOKAHEAD")) g_ctx.opt.lookahead = atoll(v);
@@ -149,6 +150,9 @@ int lair_b200_shutdown(void) {
         if (ev) cudaEventDestroy(ev);
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    for (auto& ev : c.chunk_ev)
+        if (ev) cudaEventDestroy(ev);
     pool().release();
     c = Context();
     return LAIR_B200_OK;
@@ -185,6 +189,14 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.panel_timing = value;
     } else if (!strcmp(name, "trsm_dataflow")) {
         o.trsm_dataflow = value;
+    } else if (!strcmp(name, "stream_cols")) {
+        if (value != 0 && (value < 256 || value % 256)) {
+            set_error("stream_cols must be 0 or a positive multiple of 256, got %lld", (long long)value);
+            return LAIR_B200_ERR_INVALID;
+        }
+        o.stream_cols = value;
+    } else if (!strcmp(name, "stream_join_div")) {
+        o.stream_join_div = value < 1 ? 1 : value;
     } else if (!strcmp(name, "laswp_perm")) {
         o.laswp_perm = value;
     } else if (!strcmp(name, "trsm_rb")) {
@@ -217,6 +229,8 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "panel_rpt")) *value = o.panel_rpt;
     else if (!strcmp(name, "panel_timing")) *value = o.panel_timing;
     else if (!strcmp(name, "trsm_dataflow")) *value = o.trsm_dataflow;
+    else if (!strcmp(name, "stream_cols")) *value = o.stream_cols;
+    else if (!strcmp(name, "stream_join_div")) *value = o.stream_join_div;
     else if (!strcmp(name, "laswp_perm")) *value = o.laswp_perm;
     else if (!strcmp(name, "trsm_rb")) *value = o.trsm_rb;
     else if (!strcmp(name, "fuse_swap_trsm")) *value = o.fuse_swap_trsm;

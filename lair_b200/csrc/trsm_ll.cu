@@ -15,7 +15,7 @@
 //     by the inverse of a 32 x 32 block differs in rounding only -- the parity tests bound the
 //     solution against the oracle and the residual against the oracle's.)
 // Off-diagonal work is unchanged: acc -= L_ik * X_k on DMMA m8n8k4, tiles double-buffered by
-// cp.async, CTA c owns row blocks c, c+G, ... and all CTAs are co-resident.
+// cp.async, CTA c owns row blocks c, c+G, ... and the grid fits the GPU (all CTAs become resident).
 #include "common.cuh"
 
 namespace lair {
@@ -145,6 +145,10 @@ dtrsm_ll_kernel(const double* __restrict__ LU, long long lda, int n, double* __r
     uint4* llt = ll + (size_t)ct * nblk * UNITS;
     const bool al_lu = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(LU) & 15) == 0);
 
+    // CTA x owns steps x, x+G, ...: while the chain of dependent diagonal steps is elsewhere, a CTA
+    // works ahead on its next block.  The grid never exceeds what an otherwise idle GPU keeps resident
+    // (host side), so every CTA eventually runs: kernels of the lookahead stream that share the GPU
+    // finish on their own and only delay residency.
     for (int s = blockIdx.x; s < nblk; s += gridDim.x) {
         const int blk = UPPER ? (nblk - 1 - s) : s;
         const int r0 = blk * RB;
@@ -352,7 +356,7 @@ int dtrsm_ll_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_
         LAIR_CUDA_CHECK(cudaMemset(d_units, 0, st.units * sizeof(uint4)));
         st.epoch = 1;
     }
-    // all CTAs must be co-resident (they wait on each other): grid.x * grid.y <= capacity
+    // all CTAs must be able to be resident together (they wait on each other): grid.x * grid.y <= capacity
     int gx = st.grid_cap / ntile;
     if (gx < 1) {
         set_error("trsm: %d right-hand-side tiles exceed the co-resident CTA capacity", ntile);

@@ -285,6 +285,34 @@ def test_blocked_f64_kernel_variants(lair, option, values):
         _ffi.set_option(option, default)
 
 
+@pytest.mark.parametrize("shape", [(1300, 1300), (1500, 1100), (1100, 1700)])
+def test_blocked_f64_chunked_upload(lair, shape):
+    """Host-pointer getrf with the matrix uploaded in column chunks while the sweep already runs
+    (late chunks catch up with one laswp + trsm + gemm): oracle pivots and L\\U, and the same
+    solution through gesv."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    a0 = _rand(rng, shape, np.float64)
+    ref = a0.copy()
+    piv_o, sing_o = oracle.getrf(ref)
+    default = _ffi.get_option("stream_cols")
+    try:
+        for w in (512, 0):
+            _ffi.set_option("stream_cols", w)
+            a = a0.copy()
+            piv, sing = lair.lapack.getrf(a)
+            assert piv == piv_o and sing == sing_o, (w, _first_divergence(piv, piv_o))
+            assert np.max(np.abs(a - ref)) <= 1e-9 * np.max(np.abs(ref)), w
+            if shape[0] == shape[1]:
+                b = _rand(rng, (shape[0], 3), np.float64)
+                x = lair.equation.solve(a0, b)
+                n = shape[0]
+                res = np.linalg.norm(a0 @ x - b) / (np.linalg.norm(a0) * np.linalg.norm(x) * n * np.finfo(np.float64).eps)
+                assert res < 1.0, (w, res)
+    finally:
+        _ffi.set_option("stream_cols", default)
+
+
 @pytest.mark.parametrize("shape", [(300, 300), (1000, 1000), (2000, 300), (300, 900)])
 def test_blocked_f32_matches_oracle(lair, shape):
     rng = np.random.default_rng(shape[0] + 13 * shape[1])

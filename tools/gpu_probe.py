@@ -176,6 +176,37 @@ def sec_panel():
             _ffi.set_option("panel_rpt", 2)
 
 
+def sec_e2e():
+    """Host-pointer gesv / getrf (pinned host buffers) with the matrix uploaded whole vs in column chunks."""
+    import lair_b200
+    n, nrhs = 8192, 64
+    a_host = (torch.rand(n, n, dtype=torch.float64) * 10).pin_memory()
+    b_host = (torch.rand(n, nrhs, dtype=torch.float64) * 10).pin_memory()
+    a_np, b_np = a_host.numpy(), b_host.numpy()
+    d = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        d.copy_(a_host, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d.copy_(a_host, non_blocking=True)
+    torch.cuda.synchronize()
+    out(bench="h2d_512MiB_pinned", ms=(time.perf_counter() - t0) / 3 * 1e3)
+    for w, div in ((0, 4), (512, 4), (1024, 2), (1024, 3), (1024, 4), (1024, 6), (1024, 8), (1024, 16), (2048, 4), (2048, 8)):
+        _ffi.set_option("stream_cols", w)
+        _ffi.set_option("stream_join_div", div)
+        lair_b200.equation.solve(a_np, b_np)
+        ts = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            x = lair_b200.equation.solve(a_np, b_np)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        res = float(np.linalg.norm(a_np @ x - b_np) / (np.linalg.norm(a_np) * np.linalg.norm(x) * n * 2.0 ** -53))
+        out(bench="gesv_host_e2e", stream_cols=w, join_div=div, ms_best=min(ts), ms_med=float(np.median(ts)), residual=res)
+    _ffi.set_option("stream_cols", 1024)
+    _ffi.set_option("stream_join_div", 4)
+
+
 def sec_nbsched():
     """Block-width schedule: sweep the remaining-size thresholds of the automatic nb."""
     for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
