@@ -99,12 +99,34 @@ laswp_trsm_kernel(T* __restrict__ A, long long lda, int ncols, int k0, int k, co
         if (c < cw) far[e * LDT + c] = A[(long long)s_farsrc[e] * lda + col0 + c];
     }
     __syncthreads();
-    // ---- unit-lower solve of the top tile, column sweep: row i -= L[i][kk] * row kk ----
-    for (int kk = 0; kk + 1 < k; ++kk) {
-        const int rem = k - kk - 1;
-        for (int idx = tid; idx < rem * COLS; idx += LT_THREADS) {
-            const int i = kk + 1 + idx / COLS, c = idx % COLS;
-            top[i * LDT + c] -= Ls[i * LDL + kk] * top[kk * LDT + c];
+    // ---- unit-lower solve of the top tile: row i -= L[i][kk] * row kk for kk ascending ----
+    // Groups of 8 rows: one warp solves the group's own 8 x 8 triangle (lane = column, no block
+    // barrier), then every thread applies the group to the rows below.  Each element sees exactly
+    // the updates of the plain column sweep in the same order (bit-identical), with 2 block
+    // barriers per 8 rows instead of one per row.
+    constexpr int GR = 8;
+    for (int g0 = 0; g0 < k; g0 += GR) {
+        const int gk = (k - g0) < GR ? (k - g0) : GR;
+        if (tid < COLS) {
+            T x[GR];
+#pragma unroll
+            for (int r = 0; r < GR; ++r) x[r] = (r < gk) ? top[(g0 + r) * LDT + tid] : T(0);
+#pragma unroll
+            for (int r = 1; r < GR; ++r) {
+                if (r < gk) {
+#pragma unroll
+                    for (int kk = 0; kk < r; ++kk) x[r] -= Ls[(g0 + r) * LDL + g0 + kk] * x[kk];
+                    top[(g0 + r) * LDT + tid] = x[r];
+                }
+            }
+        }
+        __syncthreads();
+        const int below = k - g0 - gk;  // rows under the group
+        for (int idx = tid; idx < below * COLS; idx += LT_THREADS) {
+            const int i = g0 + gk + idx / COLS, c = idx % COLS;
+            T v = top[i * LDT + c];
+            for (int kk = 0; kk < gk; ++kk) v -= Ls[i * LDL + g0 + kk] * top[(g0 + kk) * LDT + c];
+            top[i * LDT + c] = v;
         }
         __syncthreads();
     }

@@ -12,8 +12,9 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --ncu-step > gpurun_out/ncu_launches_${TAG}.log 2>&1
 # top kernels, full sections, from the same step
-for K in dgemm_minus panel_blocked_kernel laswp_trsm dtrsm_dataflow laswp_kernel; do
-  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${K} -s 20 -c 2 \
+for KS in dgemm_minus:4 panel_blocked_kernel:4 laswp_trsm:10 dtrsm_ll:0 laswp_kernel:4; do
+  K=${KS%%:*}; SKIP=${KS##*:}
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${K} -s ${SKIP} -c 2 \
       -o gpurun_out/prof_${K}_${TAG} -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --ncu-step > gpurun_out/ncu_${K}_${TAG}.log 2>&1
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:batched_lu32 -s 3 -c 1 \
