@@ -34,9 +34,21 @@ struct Factor {
     int swap_solve(int64_t k0, int64_t k, int64_t lc0, int64_t c0, int64_t c1, cudaStream_t st) const {
         if (c1 <= c0 || k <= 0) return LAIR_B200_OK;
         const int64_t fuse = ctx().opt.fuse_swap_trsm;
-        if (fuse == 1 || (fuse == 2 && c1 - c0 <= 512)) {
+        // (a 65..128-row triangle needs 200 KB of shared memory per CTA: worth it only for the narrow
+        //  update on the lookahead's critical path, measured)
+        if ((fuse == 1 && (k <= 64 || c1 - c0 <= 512)) || (fuse == 2 && c1 - c0 <= 512)) {
             const int rc = laswp_trsm_dev<T>(c1 - c0, A + c0, lda, k0, k, ipiv, at(k0, lc0), lda, st);
             if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
+        }
+        if (fuse == 1 && k > 64 && k <= 256) {
+            // a wide step as a chain of 64-row fused launches: each applies its own interchanges, takes
+            // the contribution of the rows solved before it (prefix) and solves its own triangle --
+            // 2..4 launches instead of laswp + the launch-per-block trsm recursion
+            for (int64_t off = 0; off < k; off += 64) {
+                const int64_t kk = (k - off) < 64 ? (k - off) : 64;
+                LAIR_CHECK(laswp_trsm_dev<T>(c1 - c0, A + c0, lda, k0 + off, kk, ipiv, at(k0 + off, lc0 + off), lda, st, off));
+            }
+            return LAIR_B200_OK;
         }
         LAIR_CHECK(swap_cols(c0, c1, k0, k0 + k, st));                                            // laswp  (getrf.rs:270-277)
         if constexpr (sizeof(T) == 8) {

@@ -146,7 +146,7 @@ struct Options {
                                 // factoring when the first has landed (0 = upload everything first)
     int64_t stream_join_div = 4; // a chunk starting at column cs joins the sweep once cs / stream_join_div columns are factored
     int64_t laswp_perm = 1;    // getrs: apply P to the right-hand sides as one collapsed permutation (laswp_perm.cu)
-    int64_t fuse_swap_trsm = 1; // block steps of width <= 64: one fused laswp+trsm launch (laswp_trsm.cu)
+    int64_t fuse_swap_trsm = 1; // block steps of width <= 128: one fused laswp+trsm launch (laswp_trsm.cu)
     int64_t trsm_dataflow = 2;  // f64 getrs: 2 flag-in-data dataflow solves with pre-inverted diagonal blocks (trsm_ll.cu),
                                 // 1 flag-word dataflow solves with substitution (trsm_dataflow.cu), 0 recursive TRSM + GEMM
     int64_t trsm_rb = 32;       // row-block height of the flag-word dataflow solves (32 or 64; same speed, measured)
@@ -208,8 +208,9 @@ template <class T> int panel_max_width(int64_t rows);
 template <class T> int panel_cluster_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 int panel_cluster_max_rows();
 int panel_cluster_timing(long long* out8, bool clear);
-// fused laswp + unit-lower trsm for k <= 64 (laswp_trsm.cu); LAIR_B200_ERR_UNSUPPORTED beyond
-template <class T> int laswp_trsm_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k, const int32_t* d_ipiv, const T* d_l, int64_t ldl, cudaStream_t s);
+// fused laswp + unit-lower trsm for k <= 128 (laswp_trsm.cu); LAIR_B200_ERR_UNSUPPORTED beyond
+template <class T> int laswp_trsm_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k, const int32_t* d_ipiv, const T* d_l, int64_t ldl, cudaStream_t s,
+                                      int64_t kp = 0);
 // 32x32 batched LU, two matrices per warp (batched_lu2.cu)
 template <class T> int getrf_batched32x2_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // one warp per CTA, branch-free column step, packed f32x2 updates (batched_lu3.cu)
