@@ -142,7 +142,13 @@ LAIR_B200_API int lair_b200_dgetrf_mg_dev(int64_t n, int64_t nb, double* d_a_loc
 LAIR_B200_API int lair_b200_sgetrf_mg_dev(int64_t n, int64_t nb, float* d_a_local, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
 
 /* Tuning knobs (also read from the environment at init: LAIR_B200_NB, LAIR_B200_SMALL_N).
- * name in {"nb", "small_n", "lookahead"}; returns LAIR_B200_ERR_INVALID for unknown names. */
+ * Behaviour: "nb" (outer block width, 0 = by remaining size), "nb_t1"/"nb_t2" (its thresholds),
+ * "small_n", "lookahead", "stream_cols"/"stream_join_div" (chunked upload of the host-pointer
+ * entry points).  Kernel variants kept for the parity tests and A/B measurements:
+ * "batched_cfg", "panel_cluster", "panel_rpt", "panel_group", "panel_exchange", "panel_w64",
+ * "panel_timing", "gemm_cfg", "fuse_swap_trsm", "trsm_dataflow", "trsm_rb", "laswp_perm"
+ * (meanings next to Options in csrc/common.cuh).  Every variant computes the same result to the
+ * parity bars of DESIGN.md section 5.  Unknown names return LAIR_B200_ERR_INVALID. */
 LAIR_B200_API int lair_b200_set_option(const char* name, int64_t value);
 LAIR_B200_API int lair_b200_get_option(const char* name, int64_t* value);
 /* Number of kernels this library has launched since init (for gpu_launches accounting). */
