@@ -138,9 +138,12 @@ struct Factor {
             }
             return LAIR_B200_OK;
         };
+        const bool chain_on_p = ctx().opt.chain_on_p != 0;
+        cudaEvent_t EM = ctx().ev[2];
         if (look) {
             LAIR_CUDA_CHECK(cudaEventRecord(EN, M));  // P starts after everything already queued on the caller's stream
             LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+            if (chain_on_p) LAIR_CUDA_CHECK(cudaEventRecord(EM, M));
         }
         int64_t jb = pick(0);
         LAIR_CHECK(rec(0, jb, P));
@@ -152,10 +155,19 @@ struct Factor {
                 LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
             }
             if (nb2 > 0) {
-                LAIR_CHECK(update(j0, jb, c0, c0 + nb2, M));  // next block first ...
-                if (look) {
-                    LAIR_CUDA_CHECK(cudaEventRecord(EN, M));
-                    LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+                if (look && chain_on_p && kmin - j0 > ctx().opt.chain_on_p) {
+                    // the whole dependent chain  panel(k) -> update(next block) -> panel(k+1)  stays on P:
+                    // no cross-stream hand-over on the critical path.  P only waits for M's previous
+                    // rest-update (which touched the next block's columns), long finished when the
+                    // panel chain is the bottleneck.
+                    LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EM, 0));
+                    LAIR_CHECK(update(j0, jb, c0, c0 + nb2, P));
+                } else {
+                    LAIR_CHECK(update(j0, jb, c0, c0 + nb2, M));  // next block first ...
+                    if (look) {
+                        LAIR_CUDA_CHECK(cudaEventRecord(EN, M));
+                        LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+                    }
                 }
                 LAIR_CHECK(rec(c0, nb2, P));                  // ... so its panel path can start under the rest
             }
@@ -163,6 +175,7 @@ struct Factor {
             LAIR_CHECK(swap_cols(0, j0, j0, j0 + jb, M));     // interchanges reach back into L (off the critical path)
             LAIR_CHECK(join_due(c0, nb2));                    // late column chunks catch up with blocks [0, c0): after
                                                               // the left interchanges, so L's rows match the pivots
+            if (look && chain_on_p) LAIR_CUDA_CHECK(cudaEventRecord(EM, M));
         }
         if (look) {  // the caller's stream sees the last panel too (already implied, kept explicit)
             LAIR_CUDA_CHECK(cudaEventRecord(EP, P));

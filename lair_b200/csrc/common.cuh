@@ -135,6 +135,8 @@ struct Options {
     int64_t nb_t2 = 10240;   // thresholds measured on B200 (profiles/r1_bench_history.md)
     int64_t small_n = 128;   // max(m, n) handled by the single-CTA exact kernel
     int64_t lookahead = 1;   // overlap panel k+1 with trailing update k
+    int64_t chain_on_p = 3072;  // lookahead: while more than this many columns remain, the next block's update runs on the
+                             // panel stream (no cross-stream hand-over on the chain); 0 = always on the main stream
     int64_t batched_cfg = -1; // tuning variant of the batched kernel, -1 = measured best per type (batched_lu.cu)
     int64_t panel_cluster = 2;  // panels that fit one cluster: 2 blocked DSMEM kernel, 1 row-per-thread DSMEM kernel, 0 global-memory exchange
     int64_t panel_rpt = 2;      // rows per thread of the blocked cluster panel kernel (1, 2, 4)

@@ -175,6 +175,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.small_n = value;
     } else if (!strcmp(name, "lookahead")) {
         o.lookahead = value;
+    } else if (!strcmp(name, "chain_on_p")) {
+        o.chain_on_p = value;
     } else if (!strcmp(name, "batched_cfg")) {
         o.batched_cfg = value;
     } else if (!strcmp(name, "panel_cluster")) {
@@ -222,6 +224,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "nb_t2")) *value = o.nb_t2;
     else if (!strcmp(name, "small_n")) *value = o.small_n;
     else if (!strcmp(name, "lookahead")) *value = o.lookahead;
+    else if (!strcmp(name, "chain_on_p")) *value = o.chain_on_p;
     else if (!strcmp(name, "batched_cfg")) *value = o.batched_cfg;
     else if (!strcmp(name, "panel_cluster")) *value = o.panel_cluster;
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;

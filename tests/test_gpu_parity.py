@@ -265,7 +265,7 @@ def test_blocked_f64_matches_oracle(lair, shape):
 
 
 @pytest.mark.parametrize("option,values", [("panel_cluster", (0, 1, 2)), ("panel_rpt", (1, 4, 2)), ("lookahead", (0, 1)), ("gemm_cfg", (1, 2, 3, 0)),
-                                           ("nb", (64, 128, 512, 256)), ("fuse_swap_trsm", (0, 2, 1)), ("panel_exchange", (0, 1)), ("panel_w64", (0, 1))])
+                                           ("nb", (64, 128, 512, 256)), ("fuse_swap_trsm", (0, 2, 1)), ("panel_exchange", (0, 1)), ("panel_w64", (0, 1)), ("chain_on_p", (0, 1))])
 def test_blocked_f64_kernel_variants(lair, option, values):
     """Every kernel variant behind a tuning option produces the oracle's pivots and L\\U."""
     from lair_b200 import _ffi

@@ -176,6 +176,28 @@ def sec_panel():
             _ffi.set_option("panel_rpt", 2)
 
 
+def sec_chain():
+    """dgetrf / sgetrf with the next-block update on the panel stream (1) or on the main stream (0)."""
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for n in (2048, 4096, 8192, 16384):
+            if pfx == "s" and n > 8192:
+                continue
+            a0 = torch.rand(n, n, dtype=dt, device="cuda") * 10
+            a = a0.clone()
+            ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+            info = torch.empty(1, dtype=torch.int32, device="cuda")
+            for v in (0, 1, 1024, 2048, 3072, 4096, 6144):
+                if v >= n:
+                    continue
+                _ffi.set_option("chain_on_p", v)
+                best, med = timeit(lambda: _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream())),
+                                   reps=5, warm=1, setup=lambda: a.copy_(a0))
+                out(bench=f"{pfx}getrf_chain", n=n, chain_on_p=v, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9,
+                    checksum=float(a.double().abs().sum()), piv_sum=int(ipiv.sum()))
+    _ffi.set_option("chain_on_p", 3072)
+
+
 def sec_e2e():
     """Host-pointer gesv / getrf (pinned host buffers) with the matrix uploaded whole vs in column chunks."""
     import lair_b200
