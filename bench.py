@@ -416,6 +416,25 @@ def run_c3(args, rank: int, world: int, local: int):
         print(json.dumps(line), flush=True)
 
 
+def _host_mem_available() -> int:
+    """Free host memory this process may pin: the smaller of the machine's available memory and the
+    cgroup's remaining allowance (a container limit that psutil does not see)."""
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        return 0
+    for lim_f, use_f in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_f).read().strip()
+            if lim != "max":
+                avail = min(avail, int(lim) - int(open(use_f).read().strip()))
+        except Exception:
+            pass
+    return max(avail, 0)
+
+
 def run_c4(args, rank: int, world: int, local: int):
     """One large f64 LU, 1-D block-cyclic columns over the ranks, NCCL panel broadcast + lookahead
     (BASELINE configs[3]; n = 65536 unless --n).  Strong scaling: the matrix is fixed, ranks split it."""
@@ -489,6 +508,40 @@ def run_c4(args, rank: int, world: int, local: int):
             pw[i], pw[p] = pw[p], pw[i]
     resid = float(np.linalg.norm(pw - z.cpu().numpy()) / (float(anorm2.sqrt()) * float(torch.linalg.norm(x)) * n * 2.0 ** -53))
 
+    # end to end through the public API (lair_b200.multigpu.getrf_mg): every step uploads the rank's
+    # column slab from pinned host memory and reads the pivots + info back.  Skipped (null, with the
+    # reason) when the slabs of all ranks would not comfortably fit the host's free memory.
+    e2e = None
+    if not args.no_e2e:
+        slab_bytes = a0.numel() * 8
+        avail = _host_mem_available()
+        fits = torch.tensor([1 if slab_bytes * world * 2 < avail else 0], device="cuda")
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+        if int(fits.item()) == 1:
+            host = torch.empty(a0.shape, dtype=torch.float64).pin_memory()
+            host.copy_(a0)
+            e2e_steps = 2
+
+            def e2e_step():
+                a.copy_(host, non_blocking=True)
+                piv, inf = multigpu.getrf_mg(a, n, nb)
+                return piv.cpu(), int(inf.cpu().item())
+
+            e2e_step()
+            _barrier(world)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                piv_h, _ = e2e_step()
+            _barrier(world)
+            t_e2e = _max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3, world) * 1e-3
+            e2e = {"value": flops / t_e2e * 1e-9, "unit": "GFLOP/s", "ms_per_step": t_e2e * 1e3,
+                   "h2d_bytes_per_step": int(slab_bytes) * world, "d2h_bytes_per_step": int(piv_h.numel() * 4 + 4) * world,
+                   "api": "lair_b200.multigpu.getrf_mg (per-rank column slab from pinned host memory; pivots + info read back)"}
+            del host
+        else:
+            e2e = {"value": None, "unit": "GFLOP/s", "skipped": f"{world} x {slab_bytes / 2**30:.1f} GiB of pinned slabs "
+                   f"vs {avail / 2**30:.0f} GiB of free host memory", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
     if rank == 0:
         peak = FP64_PEAK_TFLOPS * world
         line = {
@@ -505,7 +558,7 @@ def run_c4(args, rank: int, world: int, local: int):
                          "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": value * 1e-3 / peak,
                          "note": "whole-factorization FLOP/s per GPU (the kernel-only figure is reported by the N=1 line)", "traffic": None},
             "cpu_baseline": None,
-            "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     multigpu.finalize()
