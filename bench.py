@@ -315,7 +315,7 @@ def run_c2(args, rank: int, world: int, local: int):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10), random seed per rank",
             "config": {"workload": f"c2: getrf+getrs f64 n={n} nrhs={nrhs} per GPU (flops = 2/3 n^3 + 2 n^2 nrhs)",
                        "l2": "inputs (512 MiB per system, a fresh buffer per step) exceed the 126 MB L2",
-                       "nb": _ffi.get_option("nb") or "auto by remaining size (128 while > 5120 columns remain, then 64)", "sharding": "independent systems per rank, no collective"},
+                       "nb": _ffi.get_option("nb") or "auto by remaining size (128 while > 6144 columns remain, then 64)", "sharding": "independent systems per rank, no collective"},
             "getrf_ms": getrf_ms, "getrs_ms": getrs_ms, "getrf_gflops": 2.0 / 3.0 * n ** 3 / getrf_ms * 1e-6,
             "residual_scaled": res, "info": info_val,
             "roofline": {"bound": "tensor", "kernel": "dgemm_minus_kernel (DMMA m8n8k4 trailing update)",

@@ -107,7 +107,9 @@ struct Factor {
         // the DMMA kernel with a deeper K); measured on B200, profiles/r1_bench_history.md
         // The width follows the REMAINING size: while the trailing matrix is large the sweep is bound by
         // the GEMM on stream M (wide blocks = deeper K), once it is small by the panel chain on P.
-        const int64_t fixed_nb = ctx().opt.nb, t1 = ctx().opt.nb_t1, t2 = ctx().opt.nb_t2;
+        // (f32 keeps 64-wide blocks up to 8192 remaining columns: its 64-wide panel takes 8192 rows in one launch)
+        const int64_t fixed_nb = ctx().opt.nb, t2 = ctx().opt.nb_t2;
+        const int64_t t1 = ctx().opt.nb_t1 > 0 ? ctx().opt.nb_t1 : (sizeof(T) == 8 ? 6144 : 8192);
         auto pick = [&](int64_t j) {
             const int64_t rem = kmin - j;
             const int64_t v = fixed_nb > 0 ? fixed_nb : (rem > t2 ? 256 : (rem > t1 ? 128 : 64));

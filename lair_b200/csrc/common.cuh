@@ -131,7 +131,8 @@ template <class R> struct Ops<cx<R>> {
 // ---- process-wide context ----------------------------------------------------------------
 struct Options {
     int64_t nb = 0;          // outer block width of the blocked factorization (0 = from the remaining size, below)
-    int64_t nb_t1 = 5120;    // nb = 0: blocks are 64 wide while <= nb_t1 columns remain, 128 up to nb_t2, 256 beyond
+    int64_t nb_t1 = 0;       // nb = 0: blocks are 64 wide while <= nb_t1 columns remain (0 = 6144 for f64, 8192 for f32),
+                             // 128 wide up to nb_t2, 256 beyond
     int64_t nb_t2 = 10240;   // thresholds measured on B200 (profiles/r1_bench_history.md)
     int64_t small_n = 128;   // max(m, n) handled by the single-CTA exact kernel
     int64_t lookahead = 1;   // overlap panel k+1 with trailing update k

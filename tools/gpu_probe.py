@@ -249,7 +249,7 @@ def sec_nbsched():
                 best, med = timeit(lambda: _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream())),
                                    reps=3, warm=1, setup=lambda: a.copy_(a0))
                 out(bench=f"{pfx}getrf_nbsched", n=n, t1=t1, t2=t2, ms_best=best, ms_med=med, tflops=2 / 3 * n ** 3 / best * 1e-9)
-    _ffi.set_option("nb_t1", 5120)
+    _ffi.set_option("nb_t1", 0)
     _ffi.set_option("nb_t2", 10240)
 
 
