@@ -116,6 +116,7 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
     __shared__ KT s_wkey[NW];
     __shared__ unsigned s_wpos[NW];
     __shared__ int s_wrow[NW];  // local row index (0..PB_ROWS) of each warp's candidate
+    __shared__ int s_pos[PB_ROWS];  // final position of every local row (write-out)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // debug phase timing: accumulated in registers, flushed once at the end
@@ -427,16 +428,26 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
     }
 
     // ---- rows to their final positions ----
-    __syncthreads();
+    if (vec_ok) {
+        // coalesced: the final position of every local row goes through shared memory, then
+        // consecutive threads write consecutive 16-byte chunks of the same row (a thread writing its
+        // own row chunk by chunk makes every store instruction touch 32 different lines)
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        if (pos[r] >= 0) {
-            const T* prow = s_panel + (tid + r * TPB) * LD;
-            T* g = A + (long long)pos[r] * lda;
-            if (vec_ok) {
+        for (int r = 0; r < RPT; ++r) s_pos[tid + r * TPB] = pos[r];
+        __syncthreads();
+        constexpr int CPR = W / VEC;
+        for (int c = tid; c < PB_ROWS * CPR; c += TPB) {
+            const int r = c / CPR, cc = (c % CPR) * VEC;
+            const int p = s_pos[r];
+            if (p >= 0) *reinterpret_cast<V16*>(A + (long long)p * lda + cc) = *reinterpret_cast<const V16*>(s_panel + r * LD + cc);
+        }
+    } else {
+        __syncthreads();
 #pragma unroll
-                for (int cc = 0; cc < W / VEC; ++cc) *reinterpret_cast<V16*>(g + cc * VEC) = *reinterpret_cast<const V16*>(prow + cc * VEC);
-            } else {
+        for (int r = 0; r < RPT; ++r) {
+            if (pos[r] >= 0) {
+                const T* prow = s_panel + (tid + r * TPB) * LD;
+                T* g = A + (long long)pos[r] * lda;
                 for (int cc = 0; cc < w; ++cc) g[cc] = prow[cc];
             }
         }
