@@ -12,9 +12,11 @@
 //     always the current column; the rank-1 update writes its result one slot down), so the
 //     column step is a rolled loop with a small instruction footprint; the other columns stay
 //     parked in shared memory and are updated ONCE per sub-panel with a rank-8 update;
-//   * exchanges candidates by PULL: each CTA publishes its candidate (key, position, row) in
-//     its own shared memory, ONE cluster barrier, then every warp fetches the records and
-//     rows of its share of the peers with remote loads that are all in flight at once;
+//   * exchanges candidates without a cluster barrier in the column loop (default, ASYNC): each CTA
+//     pushes its 16-byte {key, position} record to every peer with st.async, the receiver's
+//     mbarrier counts the bytes, warp 0 picks the winner locally and PULLS only the winner's row
+//     (remote loads pipeline).  The earlier exchange (publish locally, ONE cluster barrier, every
+//     warp pulls records and rows of its share of the peers) is kept as ASYNC = false;
 //   * finds arg-max with the top 32 bits of |x| as a coarse key (one REDUX + one vote); the
 //     exact 64-bit comparison runs only among lanes that tie on the coarse key.
 // In-kernel algorithm per sub-panel s (columns 8s..8s+7) = the blocked LU recursion of the
