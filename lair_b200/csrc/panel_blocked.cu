@@ -252,12 +252,17 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                     s_mine[parity * W + lane + 32 * q] = s_panel[lrow * LD + lane + 32 * q];
                 if constexpr (ASYNC) {
                     const unsigned bar = pb_smem_u32(&s_mbar[parity]);
-                    if (lane == 0) {  // arm this column's phase: C records of 16 bytes will land here
+                    if (C == 1) {  // a single CTA: this warp is also the only consumer, no exchange
+                        if (lane == 0) {
+                            s_cand[parity][0][0] = (unsigned long long)ckey;
+                            s_cand[parity][0][1] = (unsigned long long)cpos;
+                        }
+                    } else if (lane == 0) {  // arm this column's phase: C records of 16 bytes will land here
                         unsigned long long st_;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(st_) : "r"(bar), "r"((unsigned)C * 16u) : "memory");
                     }
                     __syncwarp();  // the row above is written before any peer can learn of the record
-                    if (lane < C) {
+                    if (C > 1 && lane < C) {
                         const unsigned raddr = pb_mapa(pb_smem_u32(&s_cand[parity][rank][0]), (unsigned)lane);
                         const unsigned rbar = pb_mapa(bar, (unsigned)lane);
                         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
@@ -279,7 +284,7 @@ panel_blocked_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __
                 // (3a) warp 0 waits for the C records, decides the winner and pulls the winner's row: ONE
                 //      remote request per CTA (128 warps pulling from one SM cost ~1200 cycles, measured)
                 if (warp == 0) {
-                    pb_mbar_wait_cluster(pb_smem_u32(&s_mbar[parity]), (unsigned)(j >> 1) & 1u);
+                    if (C > 1) pb_mbar_wait_cluster(pb_smem_u32(&s_mbar[parity]), (unsigned)(j >> 1) & 1u);
                     PB_STAMP(3);
                     const KT k = lane < C ? (KT)s_cand[parity][lane][0] : (KT)0;
                     const unsigned p = lane < C ? (unsigned)s_cand[parity][lane][1] : PB_NOPOS;
