@@ -240,6 +240,7 @@ def run_c2(args, rank: int, world: int, local: int):
     e1.record()
     _barrier(world)
     ms_total = _max_over_ranks(e0.elapsed_time(e1), world)
+    _ffi.check_fault(torch.cuda.current_stream().cuda_stream)  # a timed-out device-side wait would invalidate the run
     launches = _ffi.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
@@ -472,6 +473,7 @@ def run_c4(args, rank: int, world: int, local: int):
     e1.record()
     _barrier(world)
     ms_total = _max_over_ranks(e0.elapsed_time(e1), world)
+    _ffi.check_fault(torch.cuda.current_stream().cuda_stream)  # a timed-out device-side wait would invalidate the run
     launches = _ffi.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps

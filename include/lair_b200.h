@@ -153,6 +153,14 @@ LAIR_B200_API int lair_b200_set_option(const char* name, int64_t value);
 LAIR_B200_API int lair_b200_get_option(const char* name, int64_t* value);
 /* Number of kernels this library has launched since init (for gpu_launches accounting). */
 LAIR_B200_API int64_t lair_b200_launch_count(void);
+
+/* Device-resident (_dev) calls are asynchronous.  The kernels that wait on other CTAs through
+ * global memory (panels taller than one cluster, the dataflow triangular solves of getrs) bound
+ * their waits so a lost peer cannot hang the GPU; a wait that runs out raises a device-side fault
+ * and the results are invalid.  check_fault waits for `stream`, and returns LAIR_B200_ERR_CUDA (with
+ * a message) if a fault was raised since the last check, LAIR_B200_OK otherwise.  The host-pointer
+ * entry points perform this check themselves before they return. */
+LAIR_B200_API int lair_b200_check_fault(void* stream);
 /* Optional live timing of kernel families with CUDA events on the launching stream:
  * begin() arms it, end() synchronises and accumulates, get() returns for one family
  * ("gemm", "panel", "laswp", "trsm", "batched", "small") the summed device time (ms), the

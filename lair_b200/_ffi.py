@@ -36,6 +36,7 @@ _SIGNATURES = {
     "lair_b200_set_option": [ctypes.c_char_p, i64],
     "lair_b200_get_option": [ctypes.c_char_p, ctypes.POINTER(i64)],
     "lair_b200_launch_count": [],
+    "lair_b200_check_fault": [vp],
     "lair_b200_debug_panel_timing": [ctypes.POINTER(ctypes.c_longlong), cint],
     "lair_b200_mg_unique_id": [vp],
     "lair_b200_mg_init": [cint, cint, vp],
@@ -98,6 +99,12 @@ def get_option(name: str) -> int:
 
 def launch_count() -> int:
     return int(lib().lair_b200_launch_count())
+
+
+def check_fault(stream=None) -> None:
+    """Wait for `stream` and raise if a device-side cross-CTA wait timed out since the last check
+    (the results of the asynchronous _dev calls issued before are then invalid)."""
+    check(lib().lair_b200_check_fault(ctypes.c_void_p(stream or 0)))
 
 
 def profile_begin() -> None:

@@ -98,7 +98,7 @@ static int getrf_host(int64_t m, int64_t n, T* a, int64_t rs, int64_t cs, int64_
     LAIR_CHECK(download_ipiv64(ipiv, (const int32_t*)dP, k, DevicePool::kPivots64, s));
     int32_t info32 = -1;
     LAIR_CUDA_CHECK(cudaMemcpyAsync(&info32, dI, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    LAIR_CHECK(check_fault(s));  // waits for the stream; fails loudly if a device-side wait timed out
     *info = info32;
     return LAIR_B200_OK;
 }
@@ -136,8 +136,7 @@ static int getrs_host(int64_t n, int64_t nrhs, const T* lu, int64_t lu_rs, int64
     LAIR_CHECK(upload_ipiv32<T>(ipiv, n, (int32_t*)dP, s));
     LAIR_CHECK(getrs_dev<T>(n, nrhs, (const T*)dA, ld, (const int32_t*)dP, (T*)dB, ldb, s));
     LAIR_CHECK(download_matrix<T>(x, n, nrhs, x_rs, x_cs, (const T*)dB, ldb, DevicePool::kTmpB, s));
-    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
-    return LAIR_B200_OK;
+    return check_fault(s);  // waits for the stream; fails loudly if a device-side wait timed out
 }
 
 template <class T>
@@ -168,13 +167,12 @@ static int gesv_host(int64_t n, int64_t nrhs, const T* a, int64_t a_rs, int64_t 
     LAIR_CHECK(upload_matrix<T>(b, n, nrhs, b_rs, b_cs, (T*)dB, ldb, DevicePool::kTmpB, s));
     int32_t info32 = -1;
     LAIR_CUDA_CHECK(cudaMemcpyAsync(&info32, dI, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    LAIR_CHECK(check_fault(s));
     *info = info32;
     if (info32 >= 0) return LAIR_B200_OK;  // singular: equation.rs:55-56 returns Err(Value), no solve
     LAIR_CHECK(getrs_dev<T>(n, nrhs, (const T*)dA, ld, (const int32_t*)dP, (T*)dB, ldb, s));
     LAIR_CHECK(download_matrix<T>(x, n, nrhs, x_rs, x_cs, (const T*)dB, ldb, DevicePool::kTmpB, s));
-    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
-    return LAIR_B200_OK;
+    return check_fault(s);  // waits for the stream; fails loudly if a device-side wait timed out
 }
 
 template <class T>

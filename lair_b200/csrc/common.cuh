@@ -165,6 +165,7 @@ struct Context {
     cudaStream_t stream = nullptr;        // library-owned stream for the host-pointer entry points
     cudaStream_t aux_stream = nullptr;    // second stream (lookahead / copy overlap)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int* d_fault = nullptr;               // device word raised by a timed-out cross-CTA wait (check_fault)
     cudaStream_t copy_stream = nullptr;   // host -> device column chunks of the host-pointer entry points
     static constexpr int kMaxChunks = 128;
     cudaEvent_t chunk_ev[kMaxChunks] = {};  // chunk c of the matrix has landed (created on first use)
@@ -231,8 +232,11 @@ int dtrsm_dataflow_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, 
 // all interchanges ipiv[k0..k1) on rows [k0, nrows) of a tall narrow matrix, as one permutation (laswp_perm.cu)
 template <class T> int laswp_perm_dev(int64_t nrows, int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s);
 int dtrsm_ll_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);
-// 1 if a panel exchange timed out since the last clear (results are then invalid)
-int panel_error_flag(bool clear);
+// The kernels that wait on other CTAs through global memory (tall-panel exchange, dataflow solves)
+// bound their spins so a lost peer cannot hang the GPU; a spin that runs out raises the context's
+// device fault word (Context::d_fault).  check_fault waits for `s`, reads the word and turns a raised
+// fault into LAIR_B200_ERR_CUDA with a message: such results are invalid and must not be used.
+int check_fault(cudaStream_t s);
 
 // ---- dispatch helpers ----------------------------------------------------------------------
 template <class T> int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s,

@@ -68,6 +68,8 @@ static int init_locked(int device) {
     LAIR_CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.aux_stream, cudaStreamNonBlocking, hi));
     for (auto& ev : g_ctx.ev) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     LAIR_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    LAIR_CUDA_CHECK(cudaMalloc(&g_ctx.d_fault, 64));
+    LAIR_CUDA_CHECK(cudaMemset(g_ctx.d_fault, 0, 64));
     if (const char* v = getenv("LAIR_B200_NB")) g_ctx.opt.nb = atoll(v);
     if (const char* v = getenv("LAIR_B200_SMALL_N")) g_ctx.opt.small_n = atoll(v);
     if (const char* v = getenv("LAIR_B200_LOOKAHEAD")) g_ctx.opt.lookahead = atoll(v);
@@ -89,6 +91,20 @@ int ensure_init() {
         dev = 0;
     }
     return init_locked(dev);
+}
+
+int check_fault(cudaStream_t s) {
+    Context& c = g_ctx;
+    if (!c.ready || !c.d_fault) return LAIR_B200_OK;
+    int v = 0;
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(&v, c.d_fault, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (v == 0) return LAIR_B200_OK;
+    LAIR_CUDA_CHECK(cudaMemsetAsync(c.d_fault, 0, sizeof(int), s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    set_error("a cross-CTA wait timed out on the device (fault %d: %s); the results of this call are invalid", v,
+              v == 1 ? "tall-panel pivot exchange" : "dataflow triangular solve");
+    return LAIR_B200_ERR_CUDA;
 }
 
 int ensure_scratch(size_t bytes, void** out) {
@@ -151,6 +167,7 @@ int lair_b200_shutdown(void) {
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    if (c.d_fault) cudaFree(c.d_fault);
     for (auto& ev : c.chunk_ev)
         if (ev) cudaEventDestroy(ev);
     pool().release();
@@ -247,6 +264,8 @@ int lair_b200_get_option(const char* name, int64_t* value) {
 }
 
 int64_t lair_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int lair_b200_check_fault(void* stream) { return check_fault(static_cast<cudaStream_t>(stream)); }
 
 int lair_b200_debug_panel_timing(long long* out8, int clear) {
     if (g_ctx.opt.panel_cluster >= 2) return panel_blocked_timing(out8, clear != 0);

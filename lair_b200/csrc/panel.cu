@@ -303,7 +303,7 @@ struct PanelVariant {
         const int per_cta = PANEL_TPB * RPT;
         const int grid = (int)((rows + per_cta - 1) / per_cta);
         uint4* ws = reinterpret_cast<uint4*>(c.panel_ws);
-        int* err = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(c.panel_ws) + PANEL_WS_BYTES - 256);
+        int* err = c.d_fault;  // an exchange that times out raises the context's fault word (check_fault)
         ProfScope prof(kProfPanel, s, 2.0 * (double)rows * (double)w * sizeof(T));
         panel_kernel<T, W, RPT, MINB><<<grid, PANEL_TPB, 0, s>>>(d_a, (long long)lda, (int)rows, (int)w, d_ipiv, row_base, d_info,
                                                                  step_base, ws, c.panel_seq, err);
@@ -361,15 +361,6 @@ int panel_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int
     return LAIR_B200_ERR_UNSUPPORTED;
 }
 
-int panel_error_flag(bool clear) {
-    Context& c = ctx();
-    if (!c.panel_ws) return 0;
-    int v = 0;
-    int* err = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(c.panel_ws) + PANEL_WS_BYTES - 256);
-    if (cudaMemcpy(&v, err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    if (v && clear) cudaMemset(err, 0, sizeof(int));
-    return v;
-}
 
 template int panel_max_width<float>(int64_t);
 template int panel_max_width<double>(int64_t);

@@ -288,7 +288,6 @@ struct DataflowState {
     unsigned* flags = nullptr;
     size_t cap = 0;      // flag words
     unsigned epoch = 0;
-    int* err = nullptr;
 };
 DataflowState g_df;
 
@@ -307,7 +306,6 @@ int launch_dataflow(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int
         LAIR_CUDA_CHECK(cudaMalloc(&st.flags, (cap + 1) * sizeof(unsigned)));
         LAIR_CUDA_CHECK(cudaMemset(st.flags, 0, (cap + 1) * sizeof(unsigned)));
         st.cap = cap;
-        st.err = reinterpret_cast<int*>(st.flags + cap);
         st.epoch = 0;
     }
     constexpr size_t kSmem = DfCfg<RB>::smem;
@@ -340,10 +338,10 @@ int launch_dataflow(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int
     ProfScope prof(kProfTrsm, s, (double)n * (double)n * (double)nrhs);
     if (upper)
         dtrsm_dataflow_kernel<true, RB><<<grid, DF_THREADS, kSmem, s>>>(d_lu, (long long)lda, (int)n, d_b, (long long)ldb, (int)nrhs,
-                                                                        st.flags, st.epoch, st.err);
+                                                                        st.flags, st.epoch, ctx().d_fault);
     else
         dtrsm_dataflow_kernel<false, RB><<<grid, DF_THREADS, kSmem, s>>>(d_lu, (long long)lda, (int)n, d_b, (long long)ldb, (int)nrhs,
-                                                                         st.flags, st.epoch, st.err);
+                                                                         st.flags, st.epoch, ctx().d_fault);
     LAIR_LAUNCH_CHECK();
     return LAIR_B200_OK;
 }

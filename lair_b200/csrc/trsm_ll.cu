@@ -338,7 +338,7 @@ int dtrsm_ll_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_
     }
     double* d_inv = reinterpret_cast<double*>(st.buf);
     uint4* d_units = reinterpret_cast<uint4*>(d_inv + st.inv_doubles);
-    int* d_err = reinterpret_cast<int*>(d_units + st.units);
+    int* d_err = ctx().d_fault;  // a wait that times out raises the context's fault word (check_fault)
     constexpr size_t kSmem = sizeof(LLSmem);
     if (st.grid_cap < 0) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(dtrsm_ll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));

@@ -418,6 +418,27 @@ def test_getrs_dataflow_vs_recursive(lair, n, nrhs):
         _ffi.set_option("laswp_perm", 1)
 
 
+def test_no_device_fault_after_tall_panel_and_solves(lair):
+    """The bounded cross-CTA waits (tall-panel exchange, dataflow solves) did not time out: the fault
+    word the host entry points check before returning is clear after device-resident calls too."""
+    import torch
+    from lair_b200 import _ffi
+    L = _ffi.lib()
+    m, n = 20000, 64  # taller than one cluster: the global-memory exchange panel
+    a = torch.rand(m, n, dtype=torch.float64, device="cuda")
+    ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+    info = torch.empty(1, dtype=torch.int32, device="cuda")
+    _ffi.check(L.lair_b200_dgetrf_dev(m, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), _stream()))
+    n2 = 1500
+    lu = torch.rand(n2, n2, dtype=torch.float64, device="cuda")
+    piv2 = torch.empty(n2, dtype=torch.int32, device="cuda")
+    _ffi.check(L.lair_b200_dgetrf_dev(n2, n2, lu.data_ptr(), n2, piv2.data_ptr(), info.data_ptr(), _stream()))
+    b = torch.rand(n2, 70, dtype=torch.float64, device="cuda")
+    _ffi.check(L.lair_b200_dgetrs_dev(n2, 70, lu.data_ptr(), n2, piv2.data_ptr(), b.data_ptr(), 70, _stream()))
+    _ffi.check_fault(_stream())
+    assert int(info.item()) == -1
+
+
 def test_equation_solve_end_to_end(lair):
     rng = np.random.default_rng(2)
     n = 1500
