@@ -190,6 +190,11 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.nb_t2 = value;
     } else if (!strcmp(name, "small_n")) {
         o.small_n = value;
+    } else if (!strcmp(name, "debug_raise_fault")) {
+        // test hook: raise the device fault word exactly as a timed-out wait would (tests/test_gpu_parity.py)
+        LAIR_CHECK(ensure_init());
+        const int v = (int)value;
+        LAIR_CUDA_CHECK(cudaMemcpy(g_ctx.d_fault, &v, sizeof(int), cudaMemcpyHostToDevice));
     } else if (!strcmp(name, "lookahead")) {
         o.lookahead = value;
     } else if (!strcmp(name, "chain_on_p")) {

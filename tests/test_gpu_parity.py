@@ -313,6 +313,29 @@ def test_blocked_f64_chunked_upload(lair, shape):
         _ffi.set_option("stream_cols", default)
 
 
+@pytest.mark.parametrize("shape", [(1300, 1300), (1100, 1700)])
+def test_blocked_f32_chunked_upload_backward_error(lair, shape):
+    """f32 through the chunked-upload host path (late chunks catch up with laswp + recursive trsm +
+    FFMA gemm): backward error within 10x the oracle's."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(shape[0] + shape[1])
+    a0 = _rand(rng, shape, np.float32, "normal")
+    ref = a0.copy()
+    piv_o, _ = oracle.getrf(ref)
+    be_o = backward_error(a0, ref, piv_o)
+    default = _ffi.get_option("stream_cols")
+    try:
+        for w in (512, 0):
+            _ffi.set_option("stream_cols", w)
+            a = a0.copy()
+            piv, sing = lair.lapack.getrf(a)
+            assert sing is None
+            be = backward_error(a0, a, piv)
+            assert be <= 10 * max(be_o, 0.01), (w, be, be_o)
+    finally:
+        _ffi.set_option("stream_cols", default)
+
+
 @pytest.mark.parametrize("shape", [(300, 300), (1000, 1000), (2000, 300), (300, 900)])
 def test_blocked_f32_matches_oracle(lair, shape):
     rng = np.random.default_rng(shape[0] + 13 * shape[1])
@@ -437,6 +460,28 @@ def test_no_device_fault_after_tall_panel_and_solves(lair):
     _ffi.check(L.lair_b200_dgetrs_dev(n2, 70, lu.data_ptr(), n2, piv2.data_ptr(), b.data_ptr(), 70, _stream()))
     _ffi.check_fault(_stream())
     assert int(info.item()) == -1
+
+
+def test_device_fault_is_reported_loudly(lair):
+    """A raised device fault (what a timed-out cross-CTA wait leaves behind) turns the next check --
+    explicit, or the one every host-pointer entry point makes before returning -- into an error,
+    and is cleared by it."""
+    from lair_b200 import _ffi
+    _ffi.check_fault()
+    _ffi.set_option("debug_raise_fault", 2)
+    with pytest.raises(_ffi.LairB200Error, match="timed out"):
+        _ffi.check_fault()
+    _ffi.check_fault()  # reported once, then clear
+    rng = np.random.default_rng(77)
+    a0 = _rand(rng, (300, 300), np.float64)
+    _ffi.set_option("debug_raise_fault", 1)
+    with pytest.raises(_ffi.LairB200Error, match="timed out"):
+        lair.lapack.getrf(a0.copy())
+    a = a0.copy()
+    piv, sing = lair.lapack.getrf(a)  # the library keeps working afterwards
+    ref = a0.copy()
+    piv_o, sing_o = oracle.getrf(ref)
+    assert piv == piv_o and sing == sing_o
 
 
 def test_equation_solve_end_to_end(lair):
