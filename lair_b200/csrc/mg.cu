@@ -173,8 +173,17 @@ int getrf_mg_dev(int64_t n, int64_t nb, T* d_a, int64_t lda, int32_t* d_ipiv, in
         if (lc_b <= lc_a) return LAIR_B200_OK;
         const int64_t j0 = blk * nb, w = D.width(blk), r1 = j0 + w;
         const T* wb = static_cast<const T*>(mg.wbuf[blk & 1]);
-        LAIR_CHECK(laswp_dev<T>(lc_b - lc_a, d_a + lc_a, lda, j0, r1, d_ipiv, st));
-        LAIR_CHECK(trsm_lower_unit_dev<T>(w, lc_b - lc_a, wb, w, d_a + j0 * lda + lc_a, lda, st));
+        if (ctx().opt.fuse_swap_trsm == 1 && w <= 256) {
+            // the block step as a chain of 64-row fused laswp + prefix update + trsm launches (laswp_trsm.cu),
+            // L taken from the packed panel: same arithmetic as the single-GPU sweep (blocked.cu)
+            for (int64_t off = 0; off < w; off += 64) {
+                const int64_t kk = (w - off) < 64 ? (w - off) : 64;
+                LAIR_CHECK(laswp_trsm_dev<T>(lc_b - lc_a, d_a + lc_a, lda, j0 + off, kk, d_ipiv, wb + off * w + off, w, st, off));
+            }
+        } else {
+            LAIR_CHECK(laswp_dev<T>(lc_b - lc_a, d_a + lc_a, lda, j0, r1, d_ipiv, st));
+            LAIR_CHECK(trsm_lower_unit_dev<T>(w, lc_b - lc_a, wb, w, d_a + j0 * lda + lc_a, lda, st));
+        }
         if (r1 < n)
             LAIR_CHECK(gemm_minus_dev<T>(n - r1, lc_b - lc_a, w, wb + w * w, w, d_a + j0 * lda + lc_a, lda, d_a + r1 * lda + lc_a, lda, st));
         return LAIR_B200_OK;
