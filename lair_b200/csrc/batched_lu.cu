@@ -230,13 +230,17 @@ int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t
     LAIR_REQUIRE(d_a && d_ipiv && d_info, "batched getrf: null pointer");
     const bool full = (n == 32) && (reinterpret_cast<uintptr_t>(d_a) % 16 == 0);
     // Tuning variants (option "batched_cfg", bit field): bit 0 = tighter register bound (more resident
-    // warps), bit 1 = coarse-key arg-max, bit 2 = pivot row consumed from shared memory.  The default
-    // was picked on a B200 (profiles/r1_batched_ncu.md).
+    // warps), bit 1 = coarse-key arg-max, bit 2 = pivot row consumed from shared memory; 8 / 16 / 32 / 64
+    // select the later kernels (batched_lu2/3/4.cu).  The default was picked on a B200.
     constexpr int kLo = sizeof(T) == 8 ? 3 : 5;
     constexpr int kHi = sizeof(T) == 8 ? 4 : 8;
     int64_t cfg = ctx().opt.batched_cfg;
-    if (cfg < 0) cfg = sizeof(T) == 8 ? 5 : 0;  // measured best on B200: f64 130.7 M/s (cfg 5), f32 239.6 M/s (cfg 0)
+    // measured best on B200 (profiles/r1b_batched_v4.md): f64 129-130 M/s with cfg 5 (33 is within noise),
+    // f32 265.6 M/s with cfg 33 (fourth-generation kernel, 64 registers, 32 warps / SM; cfg 0: 239 M/s)
+    if (cfg < 0) cfg = sizeof(T) == 8 ? 5 : 33;
     if (!full) return launch_batched<T, 4, kLo, false, 0>(batch, (int)n, d_a, d_ipiv, d_info, s);
+    if (cfg & 64) return getrf_batched32v5_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // f32: two matrices per warp, two rows per lane
+    if (cfg & 32) return getrf_batched32v4_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // retiring rows, NaN-poisoned lanes
     if (cfg & 16) return getrf_batched32v3_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // one warp per CTA, branch-free
     if (cfg & 8) return getrf_batched32x2_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // two matrices per warp
     switch (cfg & 7) {

@@ -221,6 +221,14 @@ template <class T> int getrf_batched32x2_dev(int64_t batch, T* d_a, int32_t* d_i
 template <class T> int getrf_batched32v3_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v3_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v3_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+// batched_lu4.cu: rows retire into the output tile, retired lanes are NaN-poisoned (no liveness bookkeeping)
+template <class T> int getrf_batched32v4_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v4_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v4_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+// batched_lu4.cu, f32: two matrices per warp, two rows per lane; anything but the plain case is redone by an exact slow routine
+template <class T> int getrf_batched32v5_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v5_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v5_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // factor one block column stored at local columns [c0, c0+w), diagonal at row r0 (blocked.cu)
 template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r0, int64_t c0, int64_t w, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
 // in-kernel blocked cluster panel (panel_blocked.cu): 8-column register sub-panels, RPT rows per thread
