@@ -410,7 +410,7 @@ def run_c3(args, rank: int, world: int, local: int):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic uniform[0,10)",
             "config": {"workload": f"c3: batched getrf {args.dtype} 10^6 x 32x32, batch sharded over ranks",
                        "l2": "per-rank input exceeds L2 at N<=4; restore copy outside the timed region"},
-            "roofline": {"bound": "hbm", "kernel": "batched_lu32_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "batched_lu32_v6_f32 / _f64 (batched_lu4.cu)", "achieved": gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -225,6 +225,10 @@ template <> int getrf_batched32v3_dev<double>(int64_t batch, double* d_a, int32_
 template <class T> int getrf_batched32v4_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v4_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v4_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+// batched_lu4.cu: straight-line column loop, evidence accumulated, anything but the plain case redone by the exact routine
+template <class T> int getrf_batched32v6_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v6_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v6_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // batched_lu4.cu, f32: two matrices per warp, two rows per lane; anything but the plain case is redone by an exact slow routine
 template <class T> int getrf_batched32v5_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v5_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
