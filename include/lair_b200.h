@@ -93,6 +93,35 @@ LAIR_B200_API int lair_b200_zgetrs(int64_t n, int64_t nrhs, const void* lu, int6
 LAIR_B200_API int lair_b200_sgesv(int64_t n, int64_t nrhs, const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* x, int64_t x_rs, int64_t x_cs, int64_t* info);
 LAIR_B200_API int lair_b200_dgesv(int64_t n, int64_t nrhs, const double* a, int64_t a_rs, int64_t a_cs, const double* b, int64_t b_rs, int64_t b_cs, double* x, int64_t x_rs, int64_t x_cs, int64_t* info);
 
+/* ---- device-resident factors: lu::Factorized (src/decomposition/lu.rs:12-20) ------------------
+ * The reference's Factorized owns L\U, the pivots and the singular flag between `from` and `solve`
+ * (lu.rs:156-171, 87-98); its getrs signature forces the host-pointer entry points above to upload
+ * L\U again for every right-hand side.  A handle keeps them in HBM instead:
+ *   lu_factor   Factorized::from: A (host, any strides, NOT modified -- the reference consumes its
+ *               argument, so the caller cannot observe it) is uploaded and factored; *info as getrf.
+ *   lu_solve    Factorized::solve for nrhs right-hand sides (b: n x nrhs through its strides; the
+ *               reference's Ix1 b is nrhs = 1).  Needs a square factorization (getrs.rs:18-20);
+ *               a singular one is solved as the reference's getrs would (division by the zero pivot).
+ *   lu_pivots   the interchange vector (int64[min(m,n)], 0-based, sequential).
+ *   lu_factors  packed L\U to the host (m x n through the strides) -- the `lu` field.
+ *   lu_view     Factorized::l / u / p / into_pl (lu.rs:42-57, 60-72, 28-39, 107-153) built by
+ *               device kernels from the resident factors; out is m x k, k x n, m x m, m x k.
+ *   lu_shape    m, n, dtype code (0 f32, 1 f64, 2 c32, 3 c64), info.
+ *   lu_destroy  frees the device buffers.  Handles are not thread-safe individually; calls
+ *               serialise on the library stream like the other host-pointer entry points.   */
+typedef struct lair_b200_lu* lair_b200_lu_t;
+enum { LAIR_LU_VIEW_L = 0, LAIR_LU_VIEW_U = 1, LAIR_LU_VIEW_P = 2, LAIR_LU_VIEW_PL = 3 };
+LAIR_B200_API int lair_b200_slu_factor(int64_t m, int64_t n, const float* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info);
+LAIR_B200_API int lair_b200_dlu_factor(int64_t m, int64_t n, const double* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info);
+LAIR_B200_API int lair_b200_clu_factor(int64_t m, int64_t n, const void* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info);
+LAIR_B200_API int lair_b200_zlu_factor(int64_t m, int64_t n, const void* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info);
+LAIR_B200_API int lair_b200_lu_solve(lair_b200_lu_t handle, int64_t nrhs, const void* b, int64_t b_rs, int64_t b_cs, void* x, int64_t x_rs, int64_t x_cs);
+LAIR_B200_API int lair_b200_lu_pivots(lair_b200_lu_t handle, int64_t* ipiv);
+LAIR_B200_API int lair_b200_lu_factors(lair_b200_lu_t handle, void* lu, int64_t rs, int64_t cs);
+LAIR_B200_API int lair_b200_lu_view(lair_b200_lu_t handle, int view, void* out, int64_t rs, int64_t cs);
+LAIR_B200_API int lair_b200_lu_shape(lair_b200_lu_t handle, int64_t* m, int64_t* n, int* dtype, int64_t* info);
+LAIR_B200_API int lair_b200_lu_destroy(lair_b200_lu_t handle);
+
 /* Batched LU of `batch` independent, contiguous, row-major n x n matrices (n <= 32),
  * i.e. `batch` calls of getrf.rs:12-27 on standard-layout inputs; results are bit-identical
  * to the reference's row-major body (getrf.rs:46-120).  ipiv: batch*n int32, info: batch

@@ -48,7 +48,17 @@ _SIGNATURES = {
     "lair_b200_profile_get": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
                               ctypes.POINTER(ctypes.c_double)],
 }
+_SIGNATURES.update({
+    # device-resident factors (lu::Factorized behind a handle)
+    "lair_b200_lu_solve": [vp, i64, vp, i64, i64, vp, i64, i64],
+    "lair_b200_lu_pivots": [vp, vp],
+    "lair_b200_lu_factors": [vp, vp, i64, i64],
+    "lair_b200_lu_view": [vp, cint, vp, i64, i64],
+    "lair_b200_lu_shape": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(cint), ctypes.POINTER(i64)],
+    "lair_b200_lu_destroy": [vp],
+})
 for _p in "sdcz":
+    _SIGNATURES[f"lair_b200_{_p}lu_factor"] = [i64, i64, vp, i64, i64, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     _SIGNATURES[f"lair_b200_{_p}getrf"] = [i64, i64, vp, i64, i64, vp, vp]
     _SIGNATURES[f"lair_b200_{_p}getrs"] = [i64, i64, vp, i64, i64, vp, vp, i64, i64, vp, i64, i64]
 for _p in "sd":

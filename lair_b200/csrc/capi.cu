@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/lair_b200.h: argument checks, dispatch between
 // the single-CTA exact kernel and the blocked factorization, host <-> device marshalling.
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "common.cuh"
@@ -197,6 +198,144 @@ static int getrf_batched_host(int64_t batch, int64_t n, T* a, int32_t* ipiv, int
     return LAIR_B200_OK;
 }
 
+
+// ---- device-resident factors: lu::Factorized (lu.rs:12-20) behind a handle ---------------------
+struct LuHandle {
+    uint32_t magic = 0x4c554844u;  // "LUHD"
+    int dtype = -1;                // 0 f32, 1 f64, 2 c32, 3 c64
+    int64_t m = 0, n = 0, k = 0, ld = 0;
+    void* d_lu = nullptr;
+    int32_t* d_ipiv = nullptr;
+    int32_t info = -1;
+};
+template <class T> struct DtypeCode;
+template <> struct DtypeCode<float> { static constexpr int v = 0; };
+template <> struct DtypeCode<double> { static constexpr int v = 1; };
+template <> struct DtypeCode<cxf> { static constexpr int v = 2; };
+template <> struct DtypeCode<cxd> { static constexpr int v = 3; };
+
+static int lu_check(const LuHandle* h) {
+    LAIR_REQUIRE(h != nullptr && h->magic == 0x4c554844u, "lu handle: null or not a handle");
+    return LAIR_B200_OK;
+}
+
+static void lu_free(LuHandle* h) {
+    if (h->d_lu) cudaFree(h->d_lu);
+    if (h->d_ipiv) cudaFree(h->d_ipiv);
+    h->magic = 0;
+    delete h;
+}
+
+// Factorized::from (lu.rs:156-171): upload + factor; nothing comes back but `info`.
+template <class T>
+static int lu_factor_host(int64_t m, int64_t n, const T* a, int64_t rs, int64_t cs, lair_b200_lu_t* out, int64_t* info) {
+    LAIR_REQUIRE(m >= 0 && n >= 0, "lu_factor: negative dimension (m=%lld, n=%lld)", (long long)m, (long long)n);
+    LAIR_REQUIRE(out != nullptr && info != nullptr, "lu_factor: null output pointer");
+    *out = nullptr;
+    *info = -1;
+    const int64_t k = m < n ? m : n;
+    LAIR_REQUIRE(k == 0 || a != nullptr, "lu_factor: null matrix");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    LuHandle* h = new (std::nothrow) LuHandle();
+    LAIR_REQUIRE(h != nullptr, "lu_factor: out of host memory");
+    h->dtype = DtypeCode<T>::v;
+    h->m = m;
+    h->n = n;
+    h->k = k;
+    h->ld = device_ld(n);
+    if (k > 0) {
+        cudaStream_t s = ctx().stream;
+        if (cudaMalloc(&h->d_lu, (size_t)m * h->ld * sizeof(T)) != cudaSuccess ||
+            cudaMalloc((void**)&h->d_ipiv, (size_t)k * sizeof(int32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            lu_free(h);
+            set_error("lu_factor: device allocation of %zu bytes failed", (size_t)m * (size_t)device_ld(n) * sizeof(T));
+            return LAIR_B200_ERR_ALLOC;
+        }
+        void* dI = nullptr;
+        int st = pool().get(DevicePool::kInfo, sizeof(int32_t), &dI);
+        const bool std_layout = is_standard_layout(m, n, rs, cs);
+        ColumnFeed feed;
+        bool chunked = false;
+        if (st == LAIR_B200_OK) st = upload_matrix_chunked<T>(a, m, n, rs, cs, (T*)h->d_lu, h->ld, &feed, &chunked);
+        if (st == LAIR_B200_OK && !chunked) st = upload_matrix<T>(a, m, n, rs, cs, (T*)h->d_lu, h->ld, DevicePool::kTmpA, s);
+        if (st == LAIR_B200_OK) st = getrf_dev<T>(m, n, (T*)h->d_lu, h->ld, h->d_ipiv, (int32_t*)dI, std_layout, s, chunked ? &feed : nullptr);
+        int32_t info32 = -1;
+        if (st == LAIR_B200_OK && cudaMemcpyAsync(&info32, dI, sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+            set_error("lu_factor: reading info failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = LAIR_B200_ERR_CUDA;
+        }
+        if (st == LAIR_B200_OK) st = check_fault(s);  // waits for the stream
+        if (st != LAIR_B200_OK) {
+            cudaStreamSynchronize(s);
+            lu_free(h);
+            return st;
+        }
+        h->info = info32;
+    }
+    *info = h->info;
+    *out = reinterpret_cast<lair_b200_lu_t>(h);
+    return LAIR_B200_OK;
+}
+
+// Factorized::solve (lu.rs:87-98) -> getrs (getrs.rs:12-38), any number of right-hand sides; L\U stays where it is.
+template <class T>
+static int lu_solve_host(const LuHandle* h, int64_t nrhs, const T* b, int64_t b_rs, int64_t b_cs, T* x, int64_t x_rs, int64_t x_cs) {
+    LAIR_REQUIRE(nrhs >= 0, "lu_solve: negative nrhs");
+    LAIR_REQUIRE(h->m == h->n, "lu_solve: needs a square factorization (%lld x %lld); getrs.rs:18-20", (long long)h->m, (long long)h->n);
+    const int64_t n = h->n;
+    if (n == 0 || nrhs == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(b && x, "lu_solve: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    const int64_t ldb = nrhs;
+    void* dB = nullptr;
+    LAIR_CHECK(pool().get(DevicePool::kRhs, (size_t)n * ldb * sizeof(T), &dB));
+    LAIR_CHECK(upload_matrix<T>(b, n, nrhs, b_rs, b_cs, (T*)dB, ldb, DevicePool::kTmpB, s));
+    LAIR_CHECK(getrs_dev<T>(n, nrhs, (const T*)h->d_lu, h->ld, h->d_ipiv, (T*)dB, ldb, s));
+    LAIR_CHECK(download_matrix<T>(x, n, nrhs, x_rs, x_cs, (const T*)dB, ldb, DevicePool::kTmpB, s));
+    return check_fault(s);
+}
+
+template <class T>
+static int lu_factors_host(const LuHandle* h, T* lu, int64_t rs, int64_t cs) {
+    if (h->m == 0 || h->n == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(lu != nullptr, "lu_factors: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    if (h->k == 0) return LAIR_B200_OK;
+    LAIR_CHECK(download_matrix<T>(lu, h->m, h->n, rs, cs, (const T*)h->d_lu, h->ld, DevicePool::kTmpA, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return LAIR_B200_OK;
+}
+
+// Factorized::{l, u, p, into_pl} (lu.rs:42-57, 60-72, 28-39, 107-153) from the resident factors.
+template <class T>
+static int lu_view_host(const LuHandle* h, int view, T* out, int64_t rs, int64_t cs) {
+    LAIR_REQUIRE(view >= LAIR_LU_VIEW_L && view <= LAIR_LU_VIEW_PL, "lu_view: unknown view %d", view);
+    const int64_t m = h->m, n = h->n, k = h->k;
+    const int64_t rows = view == LAIR_LU_VIEW_U ? k : m;
+    const int64_t cols = view == LAIR_LU_VIEW_U ? n : (view == LAIR_LU_VIEW_P ? m : k);
+    if (rows == 0 || cols == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(out != nullptr, "lu_view: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    void *dV = nullptr, *dDst = nullptr;
+    LAIR_CHECK(pool().get(DevicePool::kRhs, (size_t)rows * cols * sizeof(T), &dV));
+    if (view == LAIR_LU_VIEW_P || view == LAIR_LU_VIEW_PL) {
+        LAIR_CHECK(pool().get(DevicePool::kMisc, (size_t)m * sizeof(int32_t), &dDst));
+        LAIR_CHECK(laswp_follow_dev(m, k, h->d_ipiv, (int32_t*)dDst, s));
+    }
+    LAIR_CHECK(lu_extract_dev<T>(view, m, n, (const T*)h->d_lu, h->ld, (const int32_t*)dDst, (T*)dV, cols, s));
+    LAIR_CHECK(download_matrix<T>(out, rows, cols, rs, cs, (const T*)dV, cols, DevicePool::kTmpB, s));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return LAIR_B200_OK;
+}
+
 #define INST_DISPATCH(T)                                                                                         \
     template int getrf_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t, const ColumnFeed*); \
     template int getrs_dev<T>(int64_t, int64_t, const T*, int64_t, const int32_t*, T*, int64_t, cudaStream_t);
@@ -259,6 +398,80 @@ int lair_b200_sgetrf_batched(int64_t batch, int64_t n, float* a, int32_t* ipiv, 
 }
 int lair_b200_dgetrf_batched(int64_t batch, int64_t n, double* a, int32_t* ipiv, int32_t* info) {
     return getrf_batched_host<double>(batch, n, a, ipiv, info);
+}
+
+
+// ---- device-resident factors -------------------------------------------------------------------
+int lair_b200_slu_factor(int64_t m, int64_t n, const float* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info) {
+    return lu_factor_host<float>(m, n, a, rs, cs, handle, info);
+}
+int lair_b200_dlu_factor(int64_t m, int64_t n, const double* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info) {
+    return lu_factor_host<double>(m, n, a, rs, cs, handle, info);
+}
+int lair_b200_clu_factor(int64_t m, int64_t n, const void* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info) {
+    return lu_factor_host<cxf>(m, n, (const cxf*)a, rs, cs, handle, info);
+}
+int lair_b200_zlu_factor(int64_t m, int64_t n, const void* a, int64_t rs, int64_t cs, lair_b200_lu_t* handle, int64_t* info) {
+    return lu_factor_host<cxd>(m, n, (const cxd*)a, rs, cs, handle, info);
+}
+int lair_b200_lu_solve(lair_b200_lu_t handle, int64_t nrhs, const void* b, int64_t b_rs, int64_t b_cs, void* x, int64_t x_rs, int64_t x_cs) {
+    const LuHandle* h = reinterpret_cast<const LuHandle*>(handle);
+    LAIR_CHECK(lu_check(h));
+    switch (h->dtype) {
+        case 0: return lu_solve_host<float>(h, nrhs, (const float*)b, b_rs, b_cs, (float*)x, x_rs, x_cs);
+        case 1: return lu_solve_host<double>(h, nrhs, (const double*)b, b_rs, b_cs, (double*)x, x_rs, x_cs);
+        case 2: return lu_solve_host<cxf>(h, nrhs, (const cxf*)b, b_rs, b_cs, (cxf*)x, x_rs, x_cs);
+        default: return lu_solve_host<cxd>(h, nrhs, (const cxd*)b, b_rs, b_cs, (cxd*)x, x_rs, x_cs);
+    }
+}
+int lair_b200_lu_pivots(lair_b200_lu_t handle, int64_t* ipiv) {
+    const LuHandle* h = reinterpret_cast<const LuHandle*>(handle);
+    LAIR_CHECK(lu_check(h));
+    if (h->k == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(ipiv != nullptr, "lu_pivots: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    LAIR_CHECK(download_ipiv64(ipiv, h->d_ipiv, h->k, DevicePool::kPivots64, ctx().stream));
+    LAIR_CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+    return LAIR_B200_OK;
+}
+int lair_b200_lu_factors(lair_b200_lu_t handle, void* lu, int64_t rs, int64_t cs) {
+    const LuHandle* h = reinterpret_cast<const LuHandle*>(handle);
+    LAIR_CHECK(lu_check(h));
+    switch (h->dtype) {
+        case 0: return lu_factors_host<float>(h, (float*)lu, rs, cs);
+        case 1: return lu_factors_host<double>(h, (double*)lu, rs, cs);
+        case 2: return lu_factors_host<cxf>(h, (cxf*)lu, rs, cs);
+        default: return lu_factors_host<cxd>(h, (cxd*)lu, rs, cs);
+    }
+}
+int lair_b200_lu_view(lair_b200_lu_t handle, int view, void* out, int64_t rs, int64_t cs) {
+    const LuHandle* h = reinterpret_cast<const LuHandle*>(handle);
+    LAIR_CHECK(lu_check(h));
+    switch (h->dtype) {
+        case 0: return lu_view_host<float>(h, view, (float*)out, rs, cs);
+        case 1: return lu_view_host<double>(h, view, (double*)out, rs, cs);
+        case 2: return lu_view_host<cxf>(h, view, (cxf*)out, rs, cs);
+        default: return lu_view_host<cxd>(h, view, (cxd*)out, rs, cs);
+    }
+}
+int lair_b200_lu_shape(lair_b200_lu_t handle, int64_t* m, int64_t* n, int* dtype, int64_t* info) {
+    const LuHandle* h = reinterpret_cast<const LuHandle*>(handle);
+    LAIR_CHECK(lu_check(h));
+    if (m) *m = h->m;
+    if (n) *n = h->n;
+    if (dtype) *dtype = h->dtype;
+    if (info) *info = h->info;
+    return LAIR_B200_OK;
+}
+int lair_b200_lu_destroy(lair_b200_lu_t handle) {
+    LuHandle* h = reinterpret_cast<LuHandle*>(handle);
+    if (h == nullptr) return LAIR_B200_OK;
+    LAIR_CHECK(lu_check(h));
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    if (ctx().stream) cudaStreamSynchronize(ctx().stream);
+    lu_free(h);
+    return LAIR_B200_OK;
 }
 
 // ---- device-resident -------------------------------------------------------------------------

@@ -241,6 +241,10 @@ template <class T> int panel_blocked_max_width(int64_t rows);
 int panel_blocked_timing(long long* out8, bool clear);
 // X = T^-1 B in place, T = unit-lower / upper triangle of d_lu (trsm_dataflow.cu)
 int dtrsm_dataflow_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);
+// dst[r] = final position of the row that starts at r after the interchanges ipiv[0..k1) (laswp_perm.cu)
+int laswp_follow_dev(int64_t nrows, int64_t k1, const int32_t* d_ipiv, int32_t* d_dst, cudaStream_t s);
+// lu::Factorized::{l, u, p, into_pl} from device-resident factors (lu_extract.cu)
+template <class T> int lu_extract_dev(int mode, int64_t m, int64_t n, const T* d_lu, int64_t ld, const int32_t* d_dst, T* d_out, int64_t ldo, cudaStream_t s);
 // all interchanges ipiv[k0..k1) on rows [k0, nrows) of a tall narrow matrix, as one permutation (laswp_perm.cu)
 template <class T> int laswp_perm_dev(int64_t nrows, int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s);
 int dtrsm_ll_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);

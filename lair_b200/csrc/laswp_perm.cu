@@ -66,6 +66,16 @@ PermState g_perm;
 
 }  // namespace
 
+int laswp_follow_dev(int64_t nrows, int64_t k1, const int32_t* d_ipiv, int32_t* d_dst, cudaStream_t s) {
+    if (nrows <= 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(nrows < (1ll << 31) && k1 >= 0 && k1 <= nrows, "laswp_follow: bad shape");
+    const int grid = (int)((nrows + LP_THREADS - 1) / LP_THREADS);
+    ProfScope prof(kProfLaswp, s, (double)nrows * 8.0);
+    laswp_follow_kernel<<<grid, LP_THREADS, 0, s>>>((int)nrows, 0, (int)k1, d_ipiv, d_dst);
+    LAIR_LAUNCH_CHECK();
+    return LAIR_B200_OK;
+}
+
 // Rows [k0, nrows) of the nrows x ncols matrix d_a take the interchanges ipiv[k0 .. k1).
 template <class T>
 int laswp_perm_dev(int64_t nrows, int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s) {

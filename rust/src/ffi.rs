@@ -21,6 +21,18 @@ extern "C" {
                             b: *const c_void, b_rs: i64, b_cs: i64, x: *mut c_void, x_rs: i64, x_cs: i64) -> c_int;
     pub fn lair_b200_zgetrs(n: i64, nrhs: i64, lu: *const c_void, lu_rs: i64, lu_cs: i64, ipiv: *const i64,
                             b: *const c_void, b_rs: i64, b_cs: i64, x: *mut c_void, x_rs: i64, x_cs: i64) -> c_int;
+
+    // device-resident factors (lu::Factorized behind a handle; include/lair_b200.h)
+    pub fn lair_b200_slu_factor(m: i64, n: i64, a: *const f32, rs: i64, cs: i64, handle: *mut *mut c_void, info: *mut i64) -> c_int;
+    pub fn lair_b200_dlu_factor(m: i64, n: i64, a: *const f64, rs: i64, cs: i64, handle: *mut *mut c_void, info: *mut i64) -> c_int;
+    pub fn lair_b200_clu_factor(m: i64, n: i64, a: *const c_void, rs: i64, cs: i64, handle: *mut *mut c_void, info: *mut i64) -> c_int;
+    pub fn lair_b200_zlu_factor(m: i64, n: i64, a: *const c_void, rs: i64, cs: i64, handle: *mut *mut c_void, info: *mut i64) -> c_int;
+    pub fn lair_b200_lu_solve(handle: *mut c_void, nrhs: i64, b: *const c_void, b_rs: i64, b_cs: i64,
+                              x: *mut c_void, x_rs: i64, x_cs: i64) -> c_int;
+    pub fn lair_b200_lu_pivots(handle: *mut c_void, ipiv: *mut i64) -> c_int;
+    pub fn lair_b200_lu_factors(handle: *mut c_void, lu: *mut c_void, rs: i64, cs: i64) -> c_int;
+    pub fn lair_b200_lu_view(handle: *mut c_void, view: c_int, out: *mut c_void, rs: i64, cs: i64) -> c_int;
+    pub fn lair_b200_lu_destroy(handle: *mut c_void) -> c_int;
 }
 
 /// The reference signatures have no error channel for runtime failure, so a non-zero status

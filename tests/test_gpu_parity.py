@@ -43,7 +43,7 @@ def test_batched32_bit_exact(lair, dt, dist):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32, 33, 64, 65, 128, 129])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 32, 33, 64, 65, 128, 129, 130, 131])
 def test_batched32_every_variant_bit_exact(lair, dt, cfg):
     """Every tuning variant of the batched kernel (incl. two matrices per warp, one warp per CTA
     with packed f32x2 updates, retiring rows with NaN-poisoned lanes, odd batch, ties, singular, NaN, infinite and subnormal inputs) is
@@ -494,3 +494,91 @@ def test_equation_solve_end_to_end(lair):
     assert np.array_equal(a, a_keep)  # equation::solve factors a copy (equation.rs:54)
     res = np.linalg.norm(a @ x - b) / (np.linalg.norm(a) * np.linalg.norm(x) * n * np.finfo(np.float64).eps)
     assert res < 1.0
+
+
+# ---- device-resident lu::Factorized: handle API ------------------------
+def _host_plu(lu, piv):
+    m, n = lu.shape
+    k = min(m, n)
+    perm = np.arange(m)
+    for i, p in enumerate(piv):  # laswp on the identity (lu.rs:28-39)
+        perm[i], perm[p] = perm[p], perm[i]
+    P = np.zeros((m, m), dtype=lu.dtype)
+    P[perm, np.arange(m)] = 1
+    L = np.tril(lu[:, :k], -1)
+    L[np.arange(k), np.arange(k)] = 1
+    U = np.triu(lu[:k, :])
+    PL = np.zeros_like(L)
+    PL[perm] = L
+    return P, L, U, PL
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64, np.complex128])
+@pytest.mark.parametrize("shape", [(1, 1), (5, 5), (100, 100), (40, 17), (17, 40), (128, 3)])
+def test_lu_handle_small_matches_getrf(lair, dt, shape):
+    """Factorized keeps the factors on the device: same pivots / L\\U / singular flag as getrf on the same
+    input (bit for bit), views equal to the host restatement of lu.rs:28-72,107-153, input untouched."""
+    rng = np.random.default_rng(shape[0] * 17 + shape[1])
+    a0 = _rand(rng, shape, dt)
+    a_in = a0.copy()
+    f = lair.decomposition.lu.Factorized.from_(a_in)
+    assert np.array_equal(a_in, a0)
+    ref = a0.copy()
+    piv, sing = lair.lapack.getrf(ref)
+    assert f.pivots == piv and f.singular == sing and f.is_singular() == (sing is not None)
+    assert np.array_equal(f.lu, ref)
+    P, L, U, PL = _host_plu(ref, piv)
+    assert np.array_equal(f.p(), P) and np.array_equal(f.l(), L) and np.array_equal(f.u(), U)
+    k = min(shape)
+    assert np.array_equal(f.into_pl()[:, :k], PL)
+    if shape[0] == shape[1]:
+        b = _rand(rng, (shape[0],), dt)
+        assert np.array_equal(f.solve(b), lair.lapack.getrs(ref, piv, b))
+        bm = _rand(rng, (shape[0], 3), dt)
+        assert np.array_equal(f.solve(bm), lair.lapack.getrs(ref, piv, bm))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(700, 700), (900, 400), (400, 900)])
+def test_lu_handle_blocked_path(lair, dt, shape):
+    rng = np.random.default_rng(shape[0] + shape[1])
+    a0 = _rand(rng, shape, dt)
+    f = lair.decomposition.lu.Factorized.from_(a0 if shape[0] != 900 else np.asfortranarray(a0))
+    ref = a0.copy()
+    piv, sing = lair.lapack.getrf(ref)
+    assert f.pivots == piv and f.singular == sing
+    if shape[0] != 900:
+        assert np.array_equal(f.lu, ref)  # same kernels, same layout path
+    lu = f.lu
+    P, L, U, PL = _host_plu(lu, piv)
+    assert np.array_equal(f.p(), P) and np.array_equal(f.l(), L) and np.array_equal(f.u(), U)
+    assert np.array_equal(f.into_pl()[:, :min(shape)], PL)
+    # P^T A = L U within the backward-error bar of the blocked path
+    assert backward_error(a0, lu, piv) <= 10 * max(backward_error(a0, ref, piv), 0.01)
+    if shape[0] == shape[1]:
+        bm = _rand(rng, (shape[0], 5), dt)
+        x = f.solve(bm)
+        assert np.array_equal(x, lair.lapack.getrs(ref, piv, bm))
+        x1 = f.solve(np.ascontiguousarray(bm[:, 2]))
+        assert np.max(np.abs(x1 - x[:, 2])) <= 1e-5 * np.max(np.abs(x[:, 2]))  # 1-RHS and multi-RHS solvers differ in order
+
+
+def test_lu_handle_errors_and_edges(lair):
+    from lair_b200 import _ffi
+    from lair_b200.errors import InvalidInput
+    F = lair.decomposition.lu.Factorized
+    f = F.from_(np.zeros((0, 0)))
+    assert f.pivots == [] and not f.is_singular() and f.lu.shape == (0, 0) and f.p().shape == (0, 0)
+    f = F.from_(np.array([[1.0, 1.0], [1.0, 1.0]]))  # getrf.rs:343-347
+    assert f.singular == 1 and f.is_singular()
+    f = F.from_(np.arange(12, dtype=np.float64).reshape(4, 3) + np.eye(4, 3))
+    with pytest.raises(InvalidInput.Shape):
+        f.solve(np.zeros(3))
+    with pytest.raises(_ffi.LairB200Error):
+        f.solve(np.zeros(4))  # not square: getrs.rs:18-20
+    g = F.from_(np.eye(3))
+    assert np.array_equal(g.solve(np.array([1.0, 2.0, 3.0])), np.array([1.0, 2.0, 3.0]))
+    # several factorizations coexist
+    hs = [F.from_(np.eye(4) * (i + 1)) for i in range(5)]
+    for i, h in enumerate(hs):
+        assert np.allclose(h.solve(np.ones(4)), 1.0 / (i + 1))

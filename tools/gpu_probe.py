@@ -127,7 +127,7 @@ def sec_batched():
         a = a0.clone()
         ipiv = torch.empty(batch, 32, dtype=torch.int32, device="cuda")
         info = torch.empty(batch, dtype=torch.int32, device="cuda")
-        for cfg in (int(c) for c in os.environ.get('PROBE_CFGS', '0,5,33,64,128,129').split(',')):
+        for cfg in (int(c) for c in os.environ.get('PROBE_CFGS', '0,129,130,131').split(',')):
             _ffi.set_option("batched_cfg", cfg)
             best, med = timeit(lambda: _ffi.check(fn(batch, 32, a.data_ptr(), ipiv.data_ptr(), info.data_ptr(), stream())),
                                reps=5, setup=lambda: a.copy_(a0))
@@ -150,6 +150,36 @@ def sec_batchedone():
         torch.cuda.synchronize()
         _ffi.set_option("batched_cfg", -1)
         out(bench=f"{pfx}getrf_batched32_once", cfg=cfg)
+
+
+def sec_luhandle():
+    """lu::Factorized device-resident (handle) vs the reference-shaped getrf + getrs host path: factor once, solve k times."""
+    import lair_b200 as lair
+    import time as _t
+    n, nrhs = 8192, 64
+    rng = np.random.default_rng(0)
+    a = rng.uniform(0, 10, size=(n, n))
+    bs = [rng.uniform(0, 10, size=(n, nrhs)) for _ in range(3)]
+    for rep in range(2):  # first pass warms the pools
+        torch.cuda.synchronize(); t0 = _t.perf_counter()
+        f = lair.decomposition.lu.Factorized.from_(a)
+        torch.cuda.synchronize(); t1 = _t.perf_counter()
+        xs = [f.solve(b) for b in bs]
+        torch.cuda.synchronize(); t2 = _t.perf_counter()
+        ref = a.copy()
+        t3 = _t.perf_counter()
+        piv, sing = lair.lapack.getrf(ref)
+        t4 = _t.perf_counter()
+        ys = [lair.lapack.getrs(ref, piv, b) for b in bs]
+        t5 = _t.perf_counter()
+        l = f.l(); t6 = _t.perf_counter()
+        same = all(np.array_equal(x, y) for x, y in zip(xs, ys))
+        if rep:
+            out(bench="lu_handle_vs_host_path", n=n, nrhs=nrhs, solves=len(bs), handle_factor_ms=(t1 - t0) * 1e3,
+                handle_solve_ms_each=(t2 - t1) * 1e3 / len(bs), host_getrf_ms=(t4 - t3) * 1e3,
+                host_getrs_ms_each=(t5 - t4) * 1e3 / len(bs), view_l_ms=(t6 - t5) * 1e3, identical_solutions=bool(same),
+                note="host path = getrf (H2D + D2H of A) then getrs (H2D of L\\U per call), pageable numpy buffers")
+        del f
 
 
 def sec_panel():
