@@ -183,21 +183,47 @@ static int getrf_batched_host(int64_t batch, int64_t n, T* a, int32_t* ipiv, int
     LAIR_REQUIRE(a && ipiv && info, "getrf_batched: null pointer");
     std::lock_guard<std::mutex> lk(g_call_mu);
     LAIR_CHECK(ensure_init());
-    cudaStream_t s = ctx().stream;
+    Context& c = ctx();
+    cudaStream_t s = c.stream, up = c.copy_stream, down = c.aux_stream;
     void *dA = nullptr, *dP = nullptr, *dI = nullptr;
-    size_t abytes = (size_t)batch * n * n * sizeof(T);
-    LAIR_CHECK(pool().get(DevicePool::kMatrix, abytes, &dA));
-    LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)batch * n * sizeof(int32_t), &dP));
+    const size_t mat_bytes = (size_t)n * n * sizeof(T), piv_bytes = (size_t)n * sizeof(int32_t);
+    LAIR_CHECK(pool().get(DevicePool::kMatrix, (size_t)batch * mat_bytes, &dA));
+    LAIR_CHECK(pool().get(DevicePool::kPivots, (size_t)batch * piv_bytes, &dP));
     LAIR_CHECK(pool().get(DevicePool::kMisc, (size_t)batch * sizeof(int32_t), &dI));
-    LAIR_CUDA_CHECK(cudaMemcpyAsync(dA, a, abytes, cudaMemcpyHostToDevice, s));
-    LAIR_CHECK(getrf_batched_dev<T>(batch, n, (T*)dA, (int32_t*)dP, (int32_t*)dI, s));
-    LAIR_CUDA_CHECK(cudaMemcpyAsync(a, dA, abytes, cudaMemcpyDeviceToHost, s));
-    LAIR_CUDA_CHECK(cudaMemcpyAsync(ipiv, dP, (size_t)batch * n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    LAIR_CUDA_CHECK(cudaMemcpyAsync(info, dI, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    // The batch is independent units, so the transfers are pipelined in chunks: chunk i+1 travels host -> device
+    // (copy stream) while chunk i is factored (library stream) and chunk i-1 travels back (third stream).  With pinned
+    // host memory the call costs max(H2D, D2H) instead of their sum; pageable memory degrades to the driver's staging.
+    constexpr int kHalf = Context::kMaxChunks / 2;  // events [0, kHalf): chunk landed; [kHalf, 2 kHalf): chunk factored
+    int64_t per = 16384;
+    if ((batch + per - 1) / per > kHalf) per = (batch + kHalf - 1) / kHalf;
+    const int nchunks = (int)((batch + per - 1) / per);
+    for (int i = 0; i < 2 * kHalf; ++i)
+        if ((i % kHalf) < nchunks && !c.chunk_ev[i]) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&c.chunk_ev[i], cudaEventDisableTiming));
+    // the copy / return streams start after whatever is already queued on the library stream (buffer reuse)
+    LAIR_CUDA_CHECK(cudaEventRecord(c.ev[3], s));
+    LAIR_CUDA_CHECK(cudaStreamWaitEvent(up, c.ev[3], 0));
+    LAIR_CUDA_CHECK(cudaStreamWaitEvent(down, c.ev[3], 0));
+    for (int i = 0; i < nchunks; ++i) {
+        const int64_t b0 = (int64_t)i * per, nb = (b0 + per <= batch) ? per : (batch - b0);
+        char* dAi = (char*)dA + (size_t)b0 * mat_bytes;
+        int32_t* dPi = (int32_t*)dP + b0 * n;
+        int32_t* dIi = (int32_t*)dI + b0;
+        LAIR_CUDA_CHECK(cudaMemcpyAsync(dAi, (const char*)a + (size_t)b0 * mat_bytes, (size_t)nb * mat_bytes, cudaMemcpyHostToDevice, up));
+        LAIR_CUDA_CHECK(cudaEventRecord(c.chunk_ev[i], up));
+        LAIR_CUDA_CHECK(cudaStreamWaitEvent(s, c.chunk_ev[i], 0));
+        LAIR_CHECK(getrf_batched_dev<T>(nb, n, (T*)dAi, dPi, dIi, s));
+        LAIR_CUDA_CHECK(cudaEventRecord(c.chunk_ev[kHalf + i], s));
+        LAIR_CUDA_CHECK(cudaStreamWaitEvent(down, c.chunk_ev[kHalf + i], 0));
+        LAIR_CUDA_CHECK(cudaMemcpyAsync((char*)a + (size_t)b0 * mat_bytes, dAi, (size_t)nb * mat_bytes, cudaMemcpyDeviceToHost, down));
+        LAIR_CUDA_CHECK(cudaMemcpyAsync(ipiv + b0 * n, dPi, (size_t)nb * piv_bytes, cudaMemcpyDeviceToHost, down));
+        LAIR_CUDA_CHECK(cudaMemcpyAsync(info + b0, dIi, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, down));
+    }
+    // everything rejoins the library stream before the call returns
+    LAIR_CUDA_CHECK(cudaEventRecord(c.ev[3], down));
+    LAIR_CUDA_CHECK(cudaStreamWaitEvent(s, c.ev[3], 0));
     LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
     return LAIR_B200_OK;
 }
-
 
 // ---- device-resident factors: lu::Factorized (lu.rs:12-20) behind a handle ---------------------
 struct LuHandle {

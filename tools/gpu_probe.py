@@ -374,6 +374,25 @@ def sec_getrf():
         _ffi.set_option("lookahead", 1)
 
 
+def sec_tune8192():
+    """dgetrf n = 8192: sweep of the sweep's own thresholds (block-width switch, where the chain moves to the panel stream)."""
+    fn = L.lair_b200_dgetrf_dev
+    n = 8192
+    a0 = torch.rand(n, n, dtype=torch.float64, device="cuda") * 10
+    a = a0.clone()
+    ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+    info = torch.empty(1, dtype=torch.int32, device="cuda")
+    for t1 in (4096, 5120, 6144, 7168, 8192):
+        for cop in (0, 1024, 2048, 3072, 4096, 6144, 1 << 30):
+            _ffi.set_option("nb_t1", t1)
+            _ffi.set_option("chain_on_p", cop)
+            best, med = timeit(lambda: _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream())),
+                               reps=4, warm=1, setup=lambda: a.copy_(a0))
+            out(bench="dgetrf_tune", n=n, nb_t1=t1, chain_on_p=cop, ms_best=best, ms_med=med)
+    _ffi.set_option("nb_t1", 0)
+    _ffi.set_option("chain_on_p", 3072)
+
+
 def sec_fuse():
     """dgetrf/sgetrf with the fused laswp+trsm launch off / narrow-only / everywhere."""
     for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
