@@ -136,6 +136,10 @@ LAIR_B200_API int lair_b200_dgetrf_batched(int64_t batch, int64_t n, double* a, 
  * cudaStream_t passed as void* (NULL = default stream).  Asynchronous w.r.t. the host. */
 LAIR_B200_API int lair_b200_sgetrf_dev(int64_t m, int64_t n, float* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
 LAIR_B200_API int lair_b200_dgetrf_dev(int64_t m, int64_t n, double* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
+/* Complex<f32> / Complex<f64> (interleaved re, im; src/scalar.rs:370-386): beyond 128 x 128 a blocked sweep whose
+ * trailing update is one real GEMM on packed operands (blocked_cx.cu).                                            */
+LAIR_B200_API int lair_b200_cgetrf_dev(int64_t m, int64_t n, void* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
+LAIR_B200_API int lair_b200_zgetrf_dev(int64_t m, int64_t n, void* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
 /* In-place solve on the device: d_b (n x nrhs, row-major, ldb) is overwritten with X. */
 LAIR_B200_API int lair_b200_sgetrs_dev(int64_t n, int64_t nrhs, const float* d_lu, int64_t lda, const int32_t* d_ipiv, float* d_b, int64_t ldb, void* stream);
 LAIR_B200_API int lair_b200_dgetrs_dev(int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, const int32_t* d_ipiv, double* d_b, int64_t ldb, void* stream);

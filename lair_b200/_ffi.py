@@ -61,6 +61,8 @@ for _p in "sdcz":
     _SIGNATURES[f"lair_b200_{_p}lu_factor"] = [i64, i64, vp, i64, i64, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     _SIGNATURES[f"lair_b200_{_p}getrf"] = [i64, i64, vp, i64, i64, vp, vp]
     _SIGNATURES[f"lair_b200_{_p}getrs"] = [i64, i64, vp, i64, i64, vp, vp, i64, i64, vp, i64, i64]
+for _p in "cz":
+    _SIGNATURES[f"lair_b200_{_p}getrf_dev"] = [i64, i64, vp, i64, vp, vp, vp]
 for _p in "sd":
     _SIGNATURES[f"lair_b200_{_p}gesv"] = [i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
     _SIGNATURES[f"lair_b200_{_p}getrf_batched"] = [i64, i64, vp, vp, vp]

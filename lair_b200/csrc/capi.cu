@@ -27,8 +27,9 @@ int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_
     if constexpr (IsReal<T>::value) {
         return getrf_blocked_dev<T>(m, n, d_a, lda, d_ipiv, d_info, s, feed);
     } else {
-        // complex beyond the single-CTA limit: correct-first in-place path
-        return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
+        // complex beyond the single-CTA limit: blocked sweep, ZGEMM as one real GEMM on packed operands (blocked_cx.cu)
+        if (ctx().opt.cx_blocked == 0) return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
+        return getrf_blocked_cx_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
     }
 }
 
@@ -510,6 +511,17 @@ int lair_b200_dgetrf_dev(int64_t m, int64_t n, double* d_a, int64_t lda, int32_t
     DEV_PROLOGUE();
     LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf_dev: bad shape");
     return getrf_dev<double>(m, n, d_a, lda, d_ipiv, d_info, true, s);
+}
+// complex: interleaved (re, im) elements, Complex<f32> / Complex<f64> as num-complex lays them out
+int lair_b200_cgetrf_dev(int64_t m, int64_t n, void* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream) {
+    DEV_PROLOGUE();
+    LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf_dev: bad shape");
+    return getrf_dev<cxf>(m, n, static_cast<cxf*>(d_a), lda, d_ipiv, d_info, true, s);
+}
+int lair_b200_zgetrf_dev(int64_t m, int64_t n, void* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream) {
+    DEV_PROLOGUE();
+    LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf_dev: bad shape");
+    return getrf_dev<cxd>(m, n, static_cast<cxd*>(d_a), lda, d_ipiv, d_info, true, s);
 }
 int lair_b200_sgetrs_dev(int64_t n, int64_t nrhs, const float* d_lu, int64_t lda, const int32_t* d_ipiv, float* d_b,
                          int64_t ldb, void* stream) {

@@ -153,6 +153,7 @@ struct Options {
     int64_t trsm_dataflow = 2;  // f64 getrs: 2 flag-in-data dataflow solves with pre-inverted diagonal blocks (trsm_ll.cu),
                                 // 1 flag-word dataflow solves with substitution (trsm_dataflow.cu), 0 recursive TRSM + GEMM
     int64_t trsm_rb = 32;       // row-block height of the flag-word dataflow solves (32 or 64; same speed, measured)
+    int64_t cx_blocked = 1;     // complex beyond small_n: 1 blocked sweep (blocked_cx.cu), 2 the same with single-CTA leaf panels, 0 the single-CTA in-place kernel
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
 };
 
@@ -185,7 +186,13 @@ int ensure_scratch(size_t bytes, void** out);       // device scratch >= bytes (
 
 // ---- kernels / device-resident routines (row-major, leading dimension in elements) --------
 template <class T> int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
-template <class T> int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s);
+template <class T> int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s,
+                                       int32_t row_base = 0, bool accumulate = false);
+// blocked LU for the complex types: recursive panels, laswp on the real view, ZGEMM as one real (DMMA / FFMA) GEMM on
+// packed operands (blocked_cx.cu)
+// its leaf panel: <= 8 columns on one cluster, slabs in shared memory (panel_cx.cu); ERR_UNSUPPORTED when it does not fit
+template <class T> int panel_cx_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, bool std_layout, cudaStream_t s);
+template <class T> int getrf_blocked_cx_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s);
 template <class T> int getrs_small_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 // Columns of the device matrix that are still arriving (host -> device copies on another stream)
 // while the factorization already runs: chunk c = columns [c*chunk, (c+1)*chunk), ready[c] is

@@ -30,7 +30,7 @@ __device__ __forceinline__ void arg_better(R& v, int& i, R ov, int oi) {
 template <class T>
 __global__ void __launch_bounds__(kSmallThreads, 1)
 small_lu_kernel(T* __restrict__ A, long long lda, int m, int n, int32_t* __restrict__ ipiv, int32_t* __restrict__ info,
-                int use_smem, int ldw_smem, int std_layout) {
+                int use_smem, int ldw_smem, int std_layout, int row_base, int accumulate) {
     using O = Ops<T>;
     using R = typename O::Real;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -93,7 +93,7 @@ small_lu_kernel(T* __restrict__ A, long long lda, int m, int n, int32_t* __restr
                 // all-zero column must be row j, which is the lowest index any thread reports.
                 s_piv = (v > R(0)) ? i : j;
                 s_max = v;
-                ipiv[j] = (v > R(0)) ? i : j;
+                ipiv[j] = row_base + ((v > R(0)) ? i : j);
             }
         }
         __syncthreads();
@@ -134,7 +134,9 @@ small_lu_kernel(T* __restrict__ A, long long lda, int m, int n, int32_t* __restr
             A[r * lda + c] = W[r * ldw + c];
         }
     }
-    if (tid == 0) *info = sing;
+    // accumulate (a leaf of the blocked complex factorization, blocked_cx.cu): info keeps the LAST zero-pivot step of
+    // the whole matrix (getrf.rs:72-73), so a leaf only writes when it met one
+    if (tid == 0 && (!accumulate || sing >= 0)) *info = sing >= 0 ? row_base + sing : sing;
 }
 
 // One CTA per right-hand side; x lives in shared memory.
@@ -186,7 +188,7 @@ small_getrs_kernel(const T* __restrict__ LU, long long lda, int n, const int32_t
 
 template <class T>
 int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout,
-                    cudaStream_t s) {
+                    cudaStream_t s, int32_t row_base, bool accumulate) {
     LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf_small: bad shape m=%lld n=%lld lda=%lld", (long long)m,
                  (long long)n, (long long)lda);
     LAIR_REQUIRE(m < (1 << 20) && n < (1 << 20) && m * n < (1ll << 31), "getrf_small: matrix too large");
@@ -211,7 +213,7 @@ int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, 
     }
     ProfScope prof(kProfSmall, s, 2.0 / 3.0 * (double)m * (double)n * (double)(m < n ? m : n));
     kern<<<1, kSmallThreads, smem, s>>>(d_a, (long long)lda, (int)m, (int)n, d_ipiv, d_info, use_smem, ldw,
-                                        std_layout ? 1 : 0);
+                                        std_layout ? 1 : 0, (int)row_base, accumulate ? 1 : 0);
     LAIR_LAUNCH_CHECK();
     return LAIR_B200_OK;
 }
@@ -223,10 +225,11 @@ int getrs_small_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const i
     if (n == 0 || nrhs == 0) return LAIR_B200_OK;
     auto kern = small_getrs_kernel<T>;
     size_t smem = 2 * (size_t)n * sizeof(T);
-    LAIR_REQUIRE(smem <= 96 * 1024, "getrs_small: n=%lld too large", (long long)n);
+    const size_t limit = ctx().smem_optin > 2048 ? ctx().smem_optin - 2048 : 0;
+    LAIR_REQUIRE(smem <= limit, "getrs_small: n=%lld too large", (long long)n);
     static bool configured = false;
     if (!configured) {
-        LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         configured = true;
     }
     kern<<<(unsigned)nrhs, 256, smem, s>>>(d_lu, (long long)lda, (int)n, d_ipiv, d_b, (long long)ldb);
@@ -235,7 +238,7 @@ int getrs_small_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const i
 }
 
 #define INST(T)                                                                                              \
-    template int getrf_small_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t);  \
+    template int getrf_small_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t, int32_t, bool);  \
     template int getrs_small_dev<T>(int64_t, int64_t, const T*, int64_t, const int32_t*, T*, int64_t, cudaStream_t);
 INST(float)
 INST(double)

@@ -25,7 +25,7 @@ def lib():
 def test_header_declares_expected_surface():
     syms = _header_symbols()
     for p in "sdcz":
-        assert f"lair_b200_{p}getrf" in syms and f"lair_b200_{p}getrs" in syms
+        assert f"lair_b200_{p}getrf" in syms and f"lair_b200_{p}getrs" in syms and f"lair_b200_{p}getrf_dev" in syms
     for p in "sd":
         for name in ("gesv", "getrf_batched", "getrf_dev", "getrs_dev", "getrf_batched_dev", "laswp_dev", "trsm_dev",
                      "gemm_minus_dev"):

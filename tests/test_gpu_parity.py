@@ -582,3 +582,60 @@ def test_lu_handle_errors_and_edges(lair):
     hs = [F.from_(np.eye(4) * (i + 1)) for i in range(5)]
     for i, h in enumerate(hs):
         assert np.allclose(h.solve(np.ones(4)), 1.0 / (i + 1))
+
+
+# ---- complex beyond the single-CTA limit: blocked sweep, ZGEMM as one real GEMM (blocked_cx.cu) ----
+@pytest.mark.parametrize("dt", [np.complex128, np.complex64])
+@pytest.mark.parametrize("shape", [(129, 129), (200, 200), (500, 500), (1000, 1000), (1500, 200), (200, 700), (777, 333), (333, 777)])
+def test_complex_blocked_matches_oracle(lair, dt, shape):
+    rng = np.random.default_rng(shape[0] * 3 + shape[1])
+    a0 = _rand(rng, shape, dt)
+    a = a0.copy()
+    piv, sing = lair.lapack.getrf(a)
+    ref = a0.copy()
+    piv_o, sing_o = oracle.getrf(ref)
+    assert sing == sing_o is None
+    be, be_o = backward_error(a0, a, piv), backward_error(a0, ref, piv_o)
+    assert be <= 10 * max(be_o, 0.01), (be, be_o)
+    d = _first_divergence(piv, piv_o)
+    if dt == np.complex128:
+        assert d is None, f"first divergence at step {d}"
+        assert np.max(np.abs(a - ref)) <= 1e-9 * np.max(np.abs(ref))
+    elif d is None:  # Complex<f32>: identical pivots unless a near-tie (then the backward error above carries parity)
+        assert np.max(np.abs(a - ref)) <= 2e-2 * np.max(np.abs(ref))
+
+
+def test_complex_blocked_equals_single_cta_kernel(lair):
+    """The blocked complex sweep against the exact in-place kernel it replaces (option cx_blocked = 0): same pivots,
+    L\\U to rounding; layouts, a late zero pivot, and the solve through the factors."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(77)
+    a0 = _rand(rng, (300, 300), np.complex128, "normal")
+    out = {}
+    default = _ffi.get_option("cx_blocked")
+    try:
+        for v in (0, 2, 1):
+            _ffi.set_option("cx_blocked", v)
+            a = a0.copy()
+            out[v] = (lair.lapack.getrf(a), a)
+            f = np.asfortranarray(a0.copy())
+            pf, sf = lair.lapack.getrf(f)
+            assert pf == out[v][0][0] and sf is None
+            assert np.max(np.abs(f - a)) <= 1e-9 * np.max(np.abs(a))
+    finally:
+        _ffi.set_option("cx_blocked", default)
+    assert out[0][0] == out[1][0] == out[2][0]
+    assert np.max(np.abs(out[0][1] - out[1][1])) <= 1e-10 * np.max(np.abs(out[0][1]))
+    assert np.array_equal(out[1][1], out[2][1])  # cluster leaf == single-CTA leaf, bit for bit
+    # zero trailing block: every step from 150 on is singular, the LAST one is reported (getrf.rs:72-73)
+    z = np.zeros((300, 300), dtype=np.complex128)
+    z[:150, :150] = a0[:150, :150]
+    zz, zref = z.copy(), z.copy()
+    piv, sing = lair.lapack.getrf(zz)
+    piv_o, sing_o = oracle.getrf(zref)
+    assert sing == sing_o == 299 and piv == piv_o
+    # solve through the blocked factors
+    b = _rand(rng, (300,), np.complex128, "normal")
+    x = lair.equation.solve(a0, b)
+    res = np.linalg.norm(a0 @ x - b) / (np.linalg.norm(a0) * np.linalg.norm(x) * 300 * np.finfo(np.float64).eps)
+    assert res < 1.0, res

@@ -374,6 +374,38 @@ def sec_getrf():
         _ffi.set_option("lookahead", 1)
 
 
+def sec_cxgetrf():
+    """Complex LU device-resident: blocked sweep (blocked_cx.cu) vs the single-CTA in-place kernel it replaces."""
+    for dt, rdt, pfx in ((torch.complex128, torch.float64, "z"), (torch.complex64, torch.float32, "c")):
+        fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+        for n, modes in ((512, (1, 2, 0)), (2048, (1, 2)), (4096, (1,)), (8192, (1,))):
+            for blocked in modes:
+                _ffi.set_option("cx_blocked", blocked)
+                a0 = torch.complex(torch.rand(n, n, dtype=rdt, device="cuda") * 10, torch.rand(n, n, dtype=rdt, device="cuda") * 10)
+                a = a0.clone()
+                ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+                info = torch.empty(1, dtype=torch.int32, device="cuda")
+                _ffi.profile_begin()
+                _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream()))
+                prof = _ffi.profile_end()
+                best, med = timeit(lambda: _ffi.check(fn(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream())),
+                                   reps=3, warm=1, setup=lambda: a.copy_(a0))
+                piv = ipiv.cpu().numpy()
+                pn = np.arange(n)
+                for i, p in enumerate(piv):
+                    if i != p:
+                        pn[i], pn[p] = pn[p], pn[i]
+                PA = a0.to(torch.complex128)[torch.from_numpy(pn).cuda()]
+                LU = a.to(torch.complex128)
+                rec = (torch.tril(LU, -1) + torch.eye(n, dtype=torch.complex128, device="cuda")) @ torch.triu(LU)
+                eps = (2.0 ** -53) if rdt == torch.float64 else (2.0 ** -24)
+                be = float(torch.linalg.norm(PA - rec) / (n * eps * torch.linalg.norm(PA)))
+                out(bench=f"{pfx}getrf", n=n, blocked=blocked, ms_best=best, ms_med=med, real_tflops=8 / 3 * n ** 3 / best * 1e-9,
+                    backward_error=be, info=int(info.item()),
+                    family_ms={k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]})
+        _ffi.set_option("cx_blocked", 1)
+
+
 def sec_tune8192():
     """dgetrf n = 8192: sweep of the sweep's own thresholds (block-width switch, where the chain moves to the panel stream)."""
     fn = L.lair_b200_dgetrf_dev
