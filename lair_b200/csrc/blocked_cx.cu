@@ -156,6 +156,54 @@ int trsm_lower_unit_cx(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* d
     return trsm_lower_unit_cx<T>(k - k1, ncols, d_l + k1 * ldl + k1, ldl, d_b + k1 * ldb, ldb, s);
 }
 
+// ---- upper solve with a true divide by the diagonal, k <= 32: B <- U^-1 B (src/lapack/getrs.rs:30-36) ------------
+template <class T>
+__global__ void __launch_bounds__(TrsmCols<T>::value)
+trsm_upper_cx32_kernel(const T* __restrict__ U, long long ldu, T* __restrict__ B, long long ldb, int k, int ncols) {
+    using O = Ops<T>;
+    constexpr int kTrsmCols = TrsmCols<T>::value;
+    __shared__ T su[kTri][kTri + 1];
+    __shared__ T sb[kTri][kTrsmCols + 1];
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * kTrsmCols;
+    const int nc = min(kTrsmCols, ncols - c0);
+    for (int idx = tid; idx < k * k; idx += kTrsmCols) {
+        const int r = idx / k, c = idx - r * k;
+        if (c >= r) su[r][c] = U[(long long)r * ldu + c];
+    }
+    for (int r = 0; r < k; ++r)
+        if (tid < nc) sb[r][tid] = B[(long long)r * ldb + c0 + tid];
+    __syncthreads();
+    if (tid < nc) {
+        for (int i = k - 1; i >= 0; --i) {
+            T x = sb[i][tid];
+            for (int c = i + 1; c < k; ++c) x = O::sub(x, O::mul(su[i][c], sb[c][tid]));  // k increasing, as the reference
+            sb[i][tid] = O::div(x, su[i][i]);
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < k; ++r)
+        if (tid < nc) B[(long long)r * ldb + c0 + tid] = sb[r][tid];
+}
+
+template <class T>
+int trsm_upper_cx(int64_t k, int64_t ncols, const T* d_u, int64_t ldu, T* d_b, int64_t ldb, cudaStream_t s) {
+    if (k <= 0 || ncols <= 0) return LAIR_B200_OK;
+    if (k <= kTri) {
+        constexpr int kTrsmCols = TrsmCols<T>::value;
+        const unsigned grid = (unsigned)((ncols + kTrsmCols - 1) / kTrsmCols);
+        trsm_upper_cx32_kernel<T><<<grid, kTrsmCols, 0, s>>>(d_u, (long long)ldu, d_b, (long long)ldb, (int)k, (int)ncols);
+        LAIR_LAUNCH_CHECK();
+        return LAIR_B200_OK;
+    }
+    int64_t k1 = (k / 2) / kTri * kTri;
+    if (k1 < kTri) k1 = kTri;
+    // the bottom block first, then eliminate it from the top block: B1 -= U12 X2
+    LAIR_CHECK(trsm_upper_cx<T>(k - k1, ncols, d_u + k1 * ldu + k1, ldu, d_b + k1 * ldb, ldb, s));
+    LAIR_CHECK(gemm_minus_cx<T>(k1, ncols, k - k1, d_u + k1, ldu, d_b + k1 * ldb, ldb, d_b, ldb, s));
+    return trsm_upper_cx<T>(k1, ncols, d_u, ldu, d_b, ldb, s);
+}
+
 __global__ void set_info_kernel(int32_t* p, int32_t v) { *p = v; }
 
 template <class T>
@@ -229,6 +277,18 @@ int getrf_blocked_cx_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_i
     FactorCx<T> f{d_a, lda, m, n, d_ipiv, d_info, std_layout, s};
     return f.run();
 }
+// X = U^-1 L^-1 P B in place in d_b (n x nrhs row-major): getrs.rs:22-36 for every column, blocked.
+template <class T>
+int getrs_blocked_cx_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s) {
+    LAIR_REQUIRE(n >= 0 && nrhs >= 0 && lda >= n && ldb >= nrhs, "getrs: bad shape");
+    if (n == 0 || nrhs == 0) return LAIR_B200_OK;
+    LAIR_CHECK(laswp_cx(nrhs, d_b, ldb, 0, n, d_ipiv, s));                        // b <- P b (getrs.rs:22-23)
+    LAIR_CHECK(trsm_lower_unit_cx<T>(n, nrhs, d_lu, lda, d_b, ldb, s));           // forward  (:24-29)
+    return trsm_upper_cx<T>(n, nrhs, d_lu, lda, d_b, ldb, s);                     // backward (:30-36)
+}
+template int getrs_blocked_cx_dev<cxf>(int64_t, int64_t, const cxf*, int64_t, const int32_t*, cxf*, int64_t, cudaStream_t);
+template int getrs_blocked_cx_dev<cxd>(int64_t, int64_t, const cxd*, int64_t, const int32_t*, cxd*, int64_t, cudaStream_t);
+
 template int getrf_blocked_cx_dev<cxf>(int64_t, int64_t, cxf*, int64_t, int32_t*, int32_t*, bool, cudaStream_t);
 template int getrf_blocked_cx_dev<cxd>(int64_t, int64_t, cxd*, int64_t, int32_t*, int32_t*, bool, cudaStream_t);
 

@@ -36,9 +36,13 @@ int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_
 template <class T>
 int getrs_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb,
               cudaStream_t s) {
-    if (n <= ctx().opt.small_n || !IsReal<T>::value) return getrs_small_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
-    if constexpr (IsReal<T>::value) return getrs_blocked_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
-    return LAIR_B200_ERR_UNSUPPORTED;
+    if (n <= ctx().opt.small_n) return getrs_small_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+    if constexpr (IsReal<T>::value) {
+        return getrs_blocked_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+    } else {
+        if (ctx().opt.cx_blocked == 0) return getrs_small_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+        return getrs_blocked_cx_dev<T>(n, nrhs, d_lu, lda, d_ipiv, d_b, ldb, s);
+    }
 }
 
 static int64_t device_ld(int64_t n) {

@@ -192,6 +192,7 @@ template <class T> int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda
 // packed operands (blocked_cx.cu)
 // its leaf panel: <= 8 columns on one cluster, slabs in shared memory (panel_cx.cu); ERR_UNSUPPORTED when it does not fit
 template <class T> int panel_cx_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, bool std_layout, cudaStream_t s);
+template <class T> int getrs_blocked_cx_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int getrf_blocked_cx_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s);
 template <class T> int getrs_small_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 // Columns of the device matrix that are still arriving (host -> device copies on another stream)

@@ -639,3 +639,27 @@ def test_complex_blocked_equals_single_cta_kernel(lair):
     x = lair.equation.solve(a0, b)
     res = np.linalg.norm(a0 @ x - b) / (np.linalg.norm(a0) * np.linalg.norm(x) * 300 * np.finfo(np.float64).eps)
     assert res < 1.0, res
+
+
+@pytest.mark.parametrize("dt", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n,nrhs", [(129, 1), (300, 5), (1000, 64), (777, 3)])
+def test_complex_blocked_getrs_matches_oracle(lair, dt, n, nrhs):
+    """Blocked complex solve (laswp on the real view, 32-row triangles + packed real GEMM): residual within 10x the
+    oracle's getrs on the same factors, per column; 1-D b equals column 0 of the 2-D call."""
+    rng = np.random.default_rng(n * 5 + nrhs)
+    a0 = _rand(rng, (n, n), dt, "normal")
+    b = _rand(rng, (n, nrhs), dt, "normal")
+    lu = a0.copy()
+    piv, _ = oracle.getrf(lu)
+    x = lair.lapack.getrs(lu, piv, b)
+    assert x.shape == (n, nrhs)
+    eps = np.finfo(dt).eps / 2
+    a128, b128 = a0.astype(np.complex128), b.astype(np.complex128)
+    for r in range(0, nrhs, max(1, nrhs // 4)):
+        xo = oracle.getrs(lu, piv, np.ascontiguousarray(b[:, r]))
+        res = np.linalg.norm(a128 @ x[:, r].astype(np.complex128) - b128[:, r]) / (np.linalg.norm(a128) * np.linalg.norm(x[:, r]) * n * eps)
+        res_o = np.linalg.norm(a128 @ xo.astype(np.complex128) - b128[:, r]) / (np.linalg.norm(a128) * np.linalg.norm(xo) * n * eps)
+        assert res <= 10 * max(res_o, 0.01), (res, res_o)
+        assert np.max(np.abs(x[:, r] - xo)) <= 1e4 * eps * n * np.max(np.abs(xo))
+    one = lair.lapack.getrs(lu, piv, np.ascontiguousarray(b[:, 0]))
+    assert one.shape == (n,) and np.allclose(one, x[:, 0], rtol=0, atol=1e3 * np.finfo(dt).eps * np.max(np.abs(x)))
