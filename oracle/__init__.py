@@ -60,6 +60,12 @@ def lib() -> ctypes.CDLL:
             getattr(_lib, f"oracle_{p}gemm_minus").argtypes = [vp, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64]
             getattr(_lib, f"oracle_{p}into_pl").restype = None
             getattr(_lib, f"oracle_{p}into_pl").argtypes = [i64, i64, vp, i64, i64, vp, i64]
+            getattr(_lib, f"oracle_{p}geqrf").restype = None
+            getattr(_lib, f"oracle_{p}geqrf").argtypes = [i64, i64, vp, i64, i64, vp]
+            getattr(_lib, f"oracle_{p}qr_q").restype = None
+            getattr(_lib, f"oracle_{p}qr_q").argtypes = [i64, i64, vp, i64, i64, vp, vp]
+            getattr(_lib, f"oracle_{p}larfg").restype = None
+            getattr(_lib, f"oracle_{p}larfg").argtypes = [vp, i64, vp, i64, vp]
             getattr(_lib, f"oracle_{p}getrf_batched").restype = None
             getattr(_lib, f"oracle_{p}getrf_batched").argtypes = [i64, i64, vp, vp, vp]
         _lib.oracle_diamax.restype = i64
@@ -186,3 +192,39 @@ def time_dgetrf_dgetrs(a: np.ndarray, b: np.ndarray | None):
     lib().oracle_time_dgetrf_dgetrs(n, a.ctypes.data, piv.ctypes.data, nrhs, bb.ctypes.data, x.ctypes.data,
                                     ctypes.addressof(tg), ctypes.addressof(ts))
     return tg.value, ts.value, piv.astype(np.int64), x[:, :nrhs]
+
+
+# ---- QR path ---------------------------------------------------------------
+def larfg(alpha, x: np.ndarray):
+    """`lapack::larfg` (src/lapack/larfg.rs:9-42): x (1-D) is overwritten; returns (beta, tau)."""
+    ab = np.array([alpha], dtype=x.dtype)
+    tau = np.zeros(1, dtype=x.dtype)
+    inc = x.strides[0] // x.itemsize if x.size else 1
+    getattr(lib(), f"oracle_{_pfx(x)}larfg")(ab.ctypes.data, x.shape[0], x.ctypes.data, inc, tau.ctypes.data)
+    return float(ab[0].real), tau[0]
+
+
+def geqrf(a: np.ndarray) -> np.ndarray:
+    """In-place `lapack::geqrf` (src/lapack/geqrf.rs:9-30) on a 2-D view of any strides; returns tau."""
+    m, n = a.shape
+    rs, cs = _strides2(a)
+    tau = np.zeros(max(min(m, n), 1), dtype=a.dtype)
+    getattr(lib(), f"oracle_{_pfx(a)}geqrf")(m, n, a.ctypes.data, rs, cs, tau.ctypes.data)
+    return tau[: min(m, n)]
+
+
+def qr_q(qr: np.ndarray, tau: np.ndarray) -> np.ndarray:
+    """`qr::Factorized::q` (src/decomposition/qr.rs:27-59): the m x m unitary factor."""
+    m, n = qr.shape
+    rs, cs = _strides2(qr)
+    q = np.zeros((m, m), dtype=qr.dtype)
+    t = np.ascontiguousarray(tau, dtype=qr.dtype)
+    if t.size == 0:
+        t = np.zeros(1, dtype=qr.dtype)
+    getattr(lib(), f"oracle_{_pfx(qr)}qr_q")(m, n, qr.ctypes.data, rs, cs, t.ctypes.data, q.ctypes.data)
+    return q
+
+
+def qr_r(qr: np.ndarray) -> np.ndarray:
+    """`qr::Factorized::r` (src/decomposition/qr.rs:62-70): qr with the strict lower triangle zeroed."""
+    return np.triu(np.array(qr, copy=True))

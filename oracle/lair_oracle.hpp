@@ -492,4 +492,157 @@ inline void into_pl(A* lu, size_t nrows, size_t ncols, ptrdiff_t rs, ptrdiff_t c
     }
 }
 
+// =============================================================================
+// QR path: lapack::geqrf and decomposition::qr::Factorized.
+// Pinned by the reference's own tests (tests/golden/lair_qr_golden.json, transcribed
+// from src/lapack/larfg.rs:44-84, src/lapack/geqrf.rs:33-141,
+// src/decomposition/qr.rs:92-199) in tests/test_oracle_qr.py.
+// =============================================================================
+template <class T> inline Cx<T> conj_of(Cx<T> a) { return {a.re, -a.im}; }
+inline float conj_of(float a) { return a; }
+inline double conj_of(double a) { return a; }
+template <class T> inline Cx<T> times_real(Cx<T> a, T r) { return {a.re * r, a.im * r}; }   // Complex * T
+inline float times_real(float a, float r) { return a * r; }
+inline double times_real(double a, double r) { return a * r; }
+template <class T> inline Cx<T> over_real(Cx<T> a, T r) { return {a.re / r, a.im / r}; }    // Complex / T
+inline float over_real(float a, float r) { return a / r; }
+inline double over_real(double a, double r) { return a / r; }
+template <class T> inline Cx<T> from_real(T r, Cx<T>*) { return {r, T(0)}; }
+inline float from_real(float r, float*) { return r; }
+inline double from_real(double r, double*) { return r; }
+template <class A> inline bool is_zero_s(A a) { return a == ScalarTraits<A>::zero(); }
+
+// blas::nrm2 (src/blas/nrm2.rs:6-15): plain in-order sum of re^2 + im^2, then sqrt.
+template <class A>
+inline RealOf<A> nrm2(size_t n, const A* x, ptrdiff_t inc) {
+    using R = RealOf<A>;
+    R sum = R(0);
+    for (size_t i = 0; i < n; ++i) {
+        const A v = x[(ptrdiff_t)i * inc];
+        sum = sum + (ScalarTraits<A>::re(v) * ScalarTraits<A>::re(v) + ScalarTraits<A>::im(v) * ScalarTraits<A>::im(v));
+    }
+    return std::sqrt(sum);
+}
+// lapack::lapy3 (src/lapack.rs:63-65)
+template <class R> inline R lapy3(R x, R y, R z) { return std::sqrt(x * x + y * y + z * z); }
+
+// lapack::larfg (src/lapack/larfg.rs:9-42): x is overwritten with v[1..], returns (beta, tau).
+template <class A>
+inline void larfg(A alpha, size_t n, A* x, ptrdiff_t inc, RealOf<A>* beta_out, A* tau_out) {
+    using R = RealOf<A>;
+    using S = ScalarTraits<A>;
+    R x_norm = nrm2<A>(n, x, inc);
+    if (x_norm == R(0) && S::im(alpha) == R(0)) {
+        *beta_out = S::re(alpha);
+        *tau_out = S::zero();
+        return;
+    }
+    R beta = -std::copysign(lapy3<R>(S::re(alpha), S::im(alpha), x_norm), S::re(alpha));
+    const R eps = std::numeric_limits<R>::epsilon() / (R(1) + R(1));   // Real::eps (src/scalar.rs:393-395)
+    const R safe_min = sfmin<R>() / eps;
+    int knt = 0;
+    if (std::fabs(beta) < safe_min) {
+        const R safe_min_recip = R(1) / safe_min;
+        for (;;) {
+            ++knt;
+            for (size_t i = 0; i < n; ++i) x[(ptrdiff_t)i * inc] = times_real(x[(ptrdiff_t)i * inc], safe_min_recip);
+            beta *= safe_min_recip;
+            alpha = times_real(alpha, safe_min_recip);
+            if (std::fabs(beta) >= safe_min || knt >= 20) break;
+        }
+        x_norm = nrm2<A>(n, x, inc);
+        // literal: `alpha.square() + x_norm * x_norm` without a square root (larfg.rs:33)
+        const R asq = S::re(alpha) * S::re(alpha) + S::im(alpha) * S::im(alpha);
+        beta = -std::copysign(asq + x_norm * x_norm, S::re(alpha));
+    }
+    const A beta_a = from_real(beta, (A*)nullptr);
+    const A tau = over_real(beta_a - alpha, beta);
+    alpha = S::one() / (alpha - beta_a);
+    for (size_t i = 0; i < n; ++i) x[(ptrdiff_t)i * inc] = x[(ptrdiff_t)i * inc] * alpha;
+    beta *= std::pow(safe_min, (R)knt);
+    *beta_out = beta;
+    *tau_out = tau;
+}
+
+// lapack::larf::left (src/lapack/larf.rs:10-54): C := (I - tau v v^H) C, with the reference's
+// trimming of v's trailing zeros and C's trailing zero columns (ilalc, src/lapack/ilal.rs:6-22).
+template <class A>
+inline void larf_left(size_t nv, const A* v, ptrdiff_t incv, A tau, A* c, size_t ncols, ptrdiff_t rs, ptrdiff_t cs) {
+    using S = ScalarTraits<A>;
+    if (is_zero_s(tau)) return;
+    size_t last_v = nv;  // the reference unwraps: a zero vector panics; callers always pass v[0] = 1
+    for (size_t i = nv; i-- > 0;)
+        if (!is_zero_s(v[(ptrdiff_t)i * incv])) { last_v = i; break; }
+    if (last_v == nv) return;
+    auto at = [&](size_t r, size_t col) -> A& { return c[(ptrdiff_t)r * rs + (ptrdiff_t)col * cs]; };
+    if (ncols == 0) return;
+    size_t last_c = ncols;
+    if (!is_zero_s(at(last_v, ncols - 1))) {
+        last_c = ncols - 1;
+    } else {
+        for (size_t col = ncols; col-- > 0 && last_c == ncols;)
+            for (size_t r = 0; r <= last_v; ++r)
+                if (!is_zero_s(at(r, col))) { last_c = col; break; }
+    }
+    if (last_c == ncols) return;
+    // w = C^H v (blas::gemv::conjtrans, src/blas/gemv.rs:58-88): fold from zero, then y = 0 + 1 * sum
+    std::vector<A> w(last_c + 1);
+    for (size_t j = 0; j <= last_c; ++j) {
+        A sum = S::zero();
+        for (size_t r = 0; r <= last_v; ++r) sum = sum + conj_of(at(r, j)) * v[(ptrdiff_t)r * incv];
+        w[j] = S::zero() + S::one() * sum;
+    }
+    // C += (-tau) v w^H (blas::gerc, src/blas/gerc.rs:8-34)
+    const A alpha = -tau;
+    for (size_t i = 0; i <= last_v; ++i) {
+        const A factor = alpha * v[(ptrdiff_t)i * incv];
+        for (size_t j = 0; j <= last_c; ++j) at(i, j) = at(i, j) + factor * conj_of(w[j]);
+    }
+}
+
+// lapack::geqrf (src/lapack/geqrf.rs:9-30): in place, tau has min(m, n) entries.
+template <class A>
+inline void geqrf(A* a, size_t m, size_t n, ptrdiff_t rs, ptrdiff_t cs, A* tau) {
+    using S = ScalarTraits<A>;
+    auto at = [&](size_t r, size_t c) -> A& { return a[(ptrdiff_t)r * rs + (ptrdiff_t)c * cs]; };
+    const size_t min_dim = std::min(m, n);
+    for (size_t i = 0; i < min_dim; ++i) {
+        RealOf<A> beta;
+        A t;
+        larfg<A>(at(i, i), m - i - 1, &at(i, i) + rs, rs, &beta, &t);
+        tau[i] = t;
+        at(i, i) = S::one();
+        std::vector<A> v(m - i);
+        for (size_t r = i; r < m; ++r) v[r - i] = at(r, i);
+        if (i + 1 < n) larf_left<A>(m - i, v.data(), 1, conj_of(t), &at(i, i + 1), n - i - 1, rs, cs);
+        at(i, i) = from_real(beta, (A*)nullptr);
+    }
+}
+
+// qr::Factorized::q (src/decomposition/qr.rs:27-59): q is m x m row-major, dense.
+template <class A>
+inline void qr_q(const A* qr, size_t m, size_t n, ptrdiff_t rs, ptrdiff_t cs, const A* tau, A* q) {
+    using S = ScalarTraits<A>;
+    const size_t k = std::min(m, n);
+    auto Q = [&](size_t r, size_t c) -> A& { return q[r * m + c]; };
+    for (size_t j = 0; j < k; ++j)
+        for (size_t i = 0; i < m; ++i) Q(i, j) = qr[(ptrdiff_t)i * rs + (ptrdiff_t)j * cs];
+    for (size_t j = k; j < m; ++j) {
+        for (size_t l = 0; l < m; ++l) Q(l, j) = S::zero();
+        Q(j, j) = S::one();
+    }
+    for (size_t i = k; i-- > 0;) {
+        if (i + 1 < m) {
+            Q(i, i) = S::one();
+            std::vector<A> v(m - i);
+            for (size_t r = i; r < m; ++r) v[r - i] = Q(r, i);
+            larf_left<A>(m - i, v.data(), 1, tau[i], &Q(i, i + 1), m - i - 1, (ptrdiff_t)m, 1);
+            const A nt = -tau[i];
+            for (size_t r = i + 1; r < m; ++r) Q(r, i) = Q(r, i) * nt;
+        }
+        Q(i, i) = S::one() - tau[i];
+        for (size_t l = 0; l < i; ++l) Q(l, i) = S::zero();
+    }
+}
+
 }  // namespace lair_oracle

@@ -64,6 +64,29 @@ using namespace lair_oracle;
         }                                                                                          \
     }
 
+#define ORACLE_QR_FOR_TYPE(P, T)                                                                   \
+    /* lapack::geqrf (src/lapack/geqrf.rs:9-30) */                                                 \
+    extern "C" void oracle_##P##geqrf(int64_t m, int64_t n, void* a, int64_t rs, int64_t cs, void* tau) { \
+        geqrf<T>((T*)a, (size_t)m, (size_t)n, rs, cs, (T*)tau);                                    \
+    }                                                                                              \
+    /* qr::Factorized::q (src/decomposition/qr.rs:27-59): q = m x m row-major */                   \
+    extern "C" void oracle_##P##qr_q(int64_t m, int64_t n, const void* qr, int64_t rs, int64_t cs, \
+                                     const void* tau, void* q) {                                   \
+        qr_q<T>((const T*)qr, (size_t)m, (size_t)n, rs, cs, (const T*)tau, (T*)q);                 \
+    }                                                                                              \
+    /* lapack::larfg (src/lapack/larfg.rs:9-42): alpha_beta in: alpha, out: (beta, 0) */           \
+    extern "C" void oracle_##P##larfg(void* alpha_beta, int64_t n, void* x, int64_t inc, void* tau) { \
+        RealOf<T> beta;                                                                            \
+        T t;                                                                                       \
+        larfg<T>(*(T*)alpha_beta, (size_t)n, (T*)x, inc, &beta, &t);                               \
+        *(T*)alpha_beta = from_real(beta, (T*)nullptr);                                            \
+        *(T*)tau = t;                                                                              \
+    }
+ORACLE_QR_FOR_TYPE(s, float)
+ORACLE_QR_FOR_TYPE(d, double)
+ORACLE_QR_FOR_TYPE(c, Cx<float>)
+ORACLE_QR_FOR_TYPE(z, Cx<double>)
+
 ORACLE_FOR_TYPE(s, float)
 ORACLE_FOR_TYPE(d, double)
 ORACLE_FOR_TYPE(c, Cx<float>)
