@@ -206,6 +206,25 @@ LAIR_B200_API int lair_b200_profile_get(const char* family, double* ms, int64_t*
  * update, columns, 0}. */
 LAIR_B200_API int lair_b200_debug_panel_timing(long long* out8, int clear);
 
+/* ---- Householder QR -------------------------------------------------------------
+ * geqrf: lapack::geqrf (src/lapack/geqrf.rs:9-30) -- `a` (m x n, element strides rs / cs, any layout) is overwritten
+ * with R on and above the diagonal and the reflector vectors below it; tau receives min(m, n) entries.
+ * qr_q: qr::Factorized::q (src/decomposition/qr.rs:27-59) -- the m x m unitary factor from the factored matrix and
+ * tau, written to `q` (element strides q_rs / q_cs).  R is the upper triangle of the factored matrix (qr.rs:62-70).
+ * Complex types: interleaved (re, im).  geqrf_dev: device pointers, row-major with leading dimension lda.          */
+LAIR_B200_API int lair_b200_sgeqrf(int64_t m, int64_t n, float* a, int64_t rs, int64_t cs, float* tau);
+LAIR_B200_API int lair_b200_dgeqrf(int64_t m, int64_t n, double* a, int64_t rs, int64_t cs, double* tau);
+LAIR_B200_API int lair_b200_cgeqrf(int64_t m, int64_t n, void* a, int64_t rs, int64_t cs, void* tau);
+LAIR_B200_API int lair_b200_zgeqrf(int64_t m, int64_t n, void* a, int64_t rs, int64_t cs, void* tau);
+LAIR_B200_API int lair_b200_sqr_q(int64_t m, int64_t n, const float* qr, int64_t rs, int64_t cs, const float* tau, float* q, int64_t q_rs, int64_t q_cs);
+LAIR_B200_API int lair_b200_dqr_q(int64_t m, int64_t n, const double* qr, int64_t rs, int64_t cs, const double* tau, double* q, int64_t q_rs, int64_t q_cs);
+LAIR_B200_API int lair_b200_cqr_q(int64_t m, int64_t n, const void* qr, int64_t rs, int64_t cs, const void* tau, void* q, int64_t q_rs, int64_t q_cs);
+LAIR_B200_API int lair_b200_zqr_q(int64_t m, int64_t n, const void* qr, int64_t rs, int64_t cs, const void* tau, void* q, int64_t q_rs, int64_t q_cs);
+LAIR_B200_API int lair_b200_sgeqrf_dev(int64_t m, int64_t n, float* d_a, int64_t lda, float* d_tau, void* stream);
+LAIR_B200_API int lair_b200_dgeqrf_dev(int64_t m, int64_t n, double* d_a, int64_t lda, double* d_tau, void* stream);
+LAIR_B200_API int lair_b200_cgeqrf_dev(int64_t m, int64_t n, void* d_a, int64_t lda, void* d_tau, void* stream);
+LAIR_B200_API int lair_b200_zgeqrf_dev(int64_t m, int64_t n, void* d_a, int64_t lda, void* d_tau, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,10 @@ for _p in "sdcz":
     _SIGNATURES[f"lair_b200_{_p}lu_factor"] = [i64, i64, vp, i64, i64, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     _SIGNATURES[f"lair_b200_{_p}getrf"] = [i64, i64, vp, i64, i64, vp, vp]
     _SIGNATURES[f"lair_b200_{_p}getrs"] = [i64, i64, vp, i64, i64, vp, vp, i64, i64, vp, i64, i64]
+for _p in "sdcz":
+    _SIGNATURES[f"lair_b200_{_p}geqrf"] = [i64, i64, vp, i64, i64, vp]
+    _SIGNATURES[f"lair_b200_{_p}qr_q"] = [i64, i64, vp, i64, i64, vp, vp, i64, i64]
+    _SIGNATURES[f"lair_b200_{_p}geqrf_dev"] = [i64, i64, vp, i64, vp, vp]
 for _p in "cz":
     _SIGNATURES[f"lair_b200_{_p}getrf_dev"] = [i64, i64, vp, i64, vp, vp, vp]
 for _p in "sd":

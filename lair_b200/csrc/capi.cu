@@ -379,6 +379,52 @@ INST_DISPATCH(cxd)
 
 using namespace lair;
 
+
+// ---- host-pointer QR -------------------------------------------------------
+// lapack::geqrf (src/lapack/geqrf.rs:9-30): a (any strides) is overwritten with R and the reflectors, tau gets
+// min(m, n) entries.
+template <class T>
+static int geqrf_host(int64_t m, int64_t n, T* a, int64_t rs, int64_t cs, T* tau) {
+    LAIR_REQUIRE(m >= 0 && n >= 0, "geqrf: negative dimension (m=%lld, n=%lld)", (long long)m, (long long)n);
+    const int64_t k = m < n ? m : n;
+    if (k == 0) return LAIR_B200_OK;
+    LAIR_REQUIRE(a != nullptr && tau != nullptr, "geqrf: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    const int64_t ld = device_ld(n);
+    void *dA = nullptr, *dT = nullptr;
+    LAIR_CHECK(pool().get(DevicePool::kMatrix, (size_t)m * ld * sizeof(T), &dA));
+    LAIR_CHECK(pool().get(DevicePool::kRhs, (size_t)k * sizeof(T), &dT));
+    LAIR_CHECK(upload_matrix<T>(a, m, n, rs, cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CHECK(geqrf_dev<T>(m, n, (T*)dA, ld, (T*)dT, s));
+    LAIR_CHECK(download_matrix<T>(a, m, n, rs, cs, (const T*)dA, ld, DevicePool::kTmpA, s));
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(tau, dT, (size_t)k * sizeof(T), cudaMemcpyDeviceToHost, s));
+    return check_fault(s);
+}
+
+// qr::Factorized::q (src/decomposition/qr.rs:27-59): q (m x m, any strides) from the factored matrix and tau.
+template <class T>
+static int qr_q_host(int64_t m, int64_t n, const T* qr, int64_t rs, int64_t cs, const T* tau, T* q, int64_t q_rs, int64_t q_cs) {
+    LAIR_REQUIRE(m >= 0 && n >= 0, "qr_q: negative dimension");
+    if (m == 0) return LAIR_B200_OK;
+    const int64_t k = m < n ? m : n;
+    LAIR_REQUIRE(q != nullptr && (k == 0 || (qr != nullptr && tau != nullptr)), "qr_q: null pointer");
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    LAIR_CHECK(ensure_init());
+    cudaStream_t s = ctx().stream;
+    const int64_t ld = device_ld(n > 0 ? n : 1), ldq = device_ld(m);
+    void *dA = nullptr, *dT = nullptr, *dQ = nullptr;
+    LAIR_CHECK(pool().get(DevicePool::kMatrix, (size_t)m * ld * sizeof(T), &dA));
+    LAIR_CHECK(pool().get(DevicePool::kRhs, (size_t)(k > 0 ? k : 1) * sizeof(T), &dT));
+    LAIR_CHECK(pool().get(DevicePool::kTmpB, (size_t)m * ldq * sizeof(T), &dQ));
+    if (n > 0) LAIR_CHECK(upload_matrix<T>(qr, m, n, rs, cs, (T*)dA, ld, DevicePool::kTmpA, s));
+    if (k > 0) LAIR_CUDA_CHECK(cudaMemcpyAsync(dT, tau, (size_t)k * sizeof(T), cudaMemcpyHostToDevice, s));
+    LAIR_CHECK(qr_q_dev<T>(m, n, (const T*)dA, ld, (const T*)dT, (T*)dQ, ldq, s));
+    LAIR_CHECK(download_matrix<T>(q, m, m, q_rs, q_cs, (const T*)dQ, ldq, DevicePool::kTmpA, s));
+    return check_fault(s);
+}
+
 #define DEV_PROLOGUE()        \
     LAIR_CHECK(ensure_init()); \
     cudaStream_t s = (cudaStream_t)stream
@@ -572,5 +618,24 @@ int lair_b200_sgemm_minus_dev(int64_t m, int64_t n, int64_t k, const float* d_a,
     DEV_PROLOGUE();
     return gemm_minus_dev<float>(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, s);
 }
+
+// ---- QR ------------------------------------------------------------------------------------------
+#define LAIR_QR_ENTRY(P, T, CT)                                                                                          \
+    int lair_b200_##P##geqrf(int64_t m, int64_t n, CT* a, int64_t rs, int64_t cs, CT* tau) {                              \
+        return geqrf_host<T>(m, n, (T*)a, rs, cs, (T*)tau);                                                              \
+    }                                                                                                                    \
+    int lair_b200_##P##qr_q(int64_t m, int64_t n, const CT* qr, int64_t rs, int64_t cs, const CT* tau, CT* q, int64_t q_rs, \
+                            int64_t q_cs) {                                                                              \
+        return qr_q_host<T>(m, n, (const T*)qr, rs, cs, (const T*)tau, (T*)q, q_rs, q_cs);                               \
+    }                                                                                                                    \
+    int lair_b200_##P##geqrf_dev(int64_t m, int64_t n, CT* d_a, int64_t lda, CT* d_tau, void* stream) {                   \
+        DEV_PROLOGUE();                                                                                                  \
+        return geqrf_dev<T>(m, n, (T*)d_a, lda, (T*)d_tau, s);                                                           \
+    }
+LAIR_QR_ENTRY(s, float, float)
+LAIR_QR_ENTRY(d, double, double)
+LAIR_QR_ENTRY(c, cxf, void)
+LAIR_QR_ENTRY(z, cxd, void)
+#undef LAIR_QR_ENTRY
 
 }  // extern "C"

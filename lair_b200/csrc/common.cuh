@@ -262,6 +262,11 @@ int dtrsm_ll_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_
 // fault into LAIR_B200_ERR_CUDA with a message: such results are invalid and must not be used.
 int check_fault(cudaStream_t s);
 
+// Householder QR (qr.cu): geqrf.rs:9-30 in place on a row-major device matrix, tau on the device;
+// qr::Factorized::q (qr.rs:27-59) into a dense m x m device matrix
+template <class T> int geqrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, T* d_tau, cudaStream_t s);
+template <class T> int qr_q_dev(int64_t m, int64_t n, const T* d_qr, int64_t ldqr, const T* d_tau, T* d_q, int64_t ldq, cudaStream_t s);
+
 // ---- dispatch helpers ----------------------------------------------------------------------
 template <class T> int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s,
                                  const ColumnFeed* feed = nullptr);

@@ -1,2 +1,2 @@
-"""`lair::decomposition` -- only the LU module is in scope."""
-from . import lu  # noqa: F401
+"""`lair::decomposition` -- the LU module and the QR module."""
+from . import lu, qr  # noqa: F401

@@ -6,6 +6,7 @@ argument meaning and error behaviour follow the Rust signatures:
 * getrf(a) -> (pivots, singular)        src/lapack/getrf.rs:12-27  (in place, any strides)
 * getrs(a, p, b) -> x                   src/lapack/getrs.rs:12-38  (panics -> AssertionError)
 * laswp(ncols, a, ..., begin, piv)      src/lapack/laswp.rs:11-40  (host-side index work)
+* geqrf(a) -> tau                       src/lapack/geqrf.rs:9-30   (in place, any strides)
 
 All arithmetic happens in liblair_b200.so (CUDA, sm_100a); there is no CPU fallback.
 """
@@ -84,6 +85,38 @@ def getrs(a: np.ndarray, p, b: np.ndarray) -> np.ndarray:
     fn = getattr(_ffi.lib(), f"lair_b200_{pfx}getrs")
     _ffi.check(fn(n, nrhs, a.ctypes.data, lrs, lcs, piv.ctypes.data, b2.ctypes.data, brs, bcs, x.ctypes.data, nrhs, 1))
     return x[:, 0].copy() if one_d else x
+
+
+def geqrf(a: np.ndarray) -> np.ndarray:
+    """QR-factorize the 2-D array (view) `a` in place and return tau (geqrf.rs:9-30): R on and above the
+    diagonal, the Householder vectors below it, `tau` of length min(m, n)."""
+    if a.ndim != 2:
+        raise ValueError("geqrf expects a 2-D array")
+    if not a.flags.writeable:
+        raise ValueError("geqrf factors in place: array must be writeable")
+    m, n = a.shape
+    k = min(m, n)
+    rs, cs = _elem_strides(a)
+    tau = np.zeros(max(k, 1), dtype=a.dtype)
+    fn = getattr(_ffi.lib(), f"lair_b200_{_prefix(a)}geqrf")
+    _ffi.check(fn(m, n, a.ctypes.data, rs, cs, tau.ctypes.data))
+    return tau[:k]
+
+
+def qr_q(qr: np.ndarray, tau: np.ndarray) -> np.ndarray:
+    """The m x m unitary factor from `geqrf`'s output (qr::Factorized::q, qr.rs:27-59)."""
+    if qr.ndim != 2:
+        raise ValueError("qr_q expects a 2-D array")
+    m, n = qr.shape
+    assert len(tau) == min(m, n), "assertion failed: tau.len() == min(nrows, ncols)"
+    q = np.empty((m, m), dtype=qr.dtype)
+    t = np.ascontiguousarray(tau, dtype=qr.dtype)
+    if t.size == 0:
+        t = np.zeros(1, dtype=qr.dtype)
+    rs, cs = _elem_strides(qr)
+    fn = getattr(_ffi.lib(), f"lair_b200_{_prefix(qr)}qr_q")
+    _ffi.check(fn(m, n, qr.ctypes.data, rs, cs, t.ctypes.data, q.ctypes.data, m, 1))
+    return q
 
 
 def laswp(a: np.ndarray, piv, begin: int = 0) -> None:
