@@ -154,6 +154,7 @@ struct Options {
                                 // 1 flag-word dataflow solves with substitution (trsm_dataflow.cu), 0 recursive TRSM + GEMM
     int64_t trsm_rb = 32;       // row-block height of the flag-word dataflow solves (32 or 64; same speed, measured)
     int64_t cx_blocked = 1;     // complex beyond small_n: 1 blocked sweep (blocked_cx.cu), 2 the same with single-CTA leaf panels, 0 the single-CTA in-place kernel
+    int64_t qr_blocked = 1;     // f32 / f64 geqrf with min(m, n) >= 64: 1 compact-WY blocks (qr_blocked.cu), 0 one reflector at a time
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
 };
 
@@ -265,6 +266,7 @@ int check_fault(cudaStream_t s);
 // Householder QR (qr.cu): geqrf.rs:9-30 in place on a row-major device matrix, tau on the device;
 // qr::Factorized::q (qr.rs:27-59) into a dense m x m device matrix
 template <class T> int geqrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, T* d_tau, cudaStream_t s);
+template <class R> int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaStream_t s);  // f32 / f64 (qr_blocked.cu)
 template <class T> int qr_q_dev(int64_t m, int64_t n, const T* d_qr, int64_t ldqr, const T* d_tau, T* d_q, int64_t ldq, cudaStream_t s);
 
 // ---- dispatch helpers ----------------------------------------------------------------------

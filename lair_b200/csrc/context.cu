@@ -203,6 +203,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.batched_cfg = value;
     } else if (!strcmp(name, "panel_cluster")) {
         o.panel_cluster = value;
+    } else if (!strcmp(name, "qr_blocked")) {
+        o.qr_blocked = value;
     } else if (!strcmp(name, "cx_blocked")) {
         o.cx_blocked = value;
     } else if (!strcmp(name, "gemm_cfg")) {
@@ -251,6 +253,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "chain_on_p")) *value = o.chain_on_p;
     else if (!strcmp(name, "batched_cfg")) *value = o.batched_cfg;
     else if (!strcmp(name, "panel_cluster")) *value = o.panel_cluster;
+    else if (!strcmp(name, "qr_blocked")) *value = o.qr_blocked;
     else if (!strcmp(name, "cx_blocked")) *value = o.cx_blocked;
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
     else if (!strcmp(name, "panel_group")) *value = o.panel_group;

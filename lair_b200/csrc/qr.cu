@@ -202,6 +202,13 @@ int geqrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, T* d_tau, cudaStream_t 
     LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "geqrf: bad shape m=%lld n=%lld lda=%lld", (long long)m, (long long)n, (long long)lda);
     LAIR_REQUIRE(m < (1ll << 31) && n < (1ll << 31), "geqrf: dimension too large");
     const int64_t k = m < n ? m : n;
+    if constexpr (!Ops<T>::is_complex) {
+        // f32 / f64 beyond a few panels: compact-WY blocks on the cluster panel + GEMM machinery (qr_blocked.cu)
+        if (ctx().opt.qr_blocked != 0 && k >= 64) {
+            const int rc = geqrf_blocked_dev<T>(m, n, d_a, lda, d_tau, s);
+            if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
+        }
+    }
     ProfScope prof(kProfSmall, s, 2.0 * (double)m * (double)n * (double)k);
     for (int64_t i = 0; i < k; ++i) {
         T* aii = d_a + i * lda + i;

@@ -95,3 +95,35 @@ def test_geqrf_edges(lair):
     # non-square Factorized: shapes of q and r (qr.rs:135-199)
     f = lair.decomposition.qr.Factorized.from_(np.arange(12, dtype=np.float64).reshape(3, 4) + np.eye(3, 4))
     assert f.q().shape == (3, 3) and f.r().shape == (3, 4) and f.tau.shape == (3,)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(64, 64), (200, 200), (1000, 1000), (3000, 200), (200, 900), (2049, 97), (777, 333)])
+def test_geqrf_blocked_equals_unblocked(lair, dt, shape):
+    """Compact-WY blocks (cluster panel + three GEMMs per block, qr_blocked.cu) against the one-reflector-at-a-time
+    loop (qr.cu) and the oracle: R, the reflectors and tau to rounding; factorization error and orthogonality within
+    10x the oracle's."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(shape[0] + 13 * shape[1])
+    a0 = _rand(rng, shape, dt, "normal")
+    out = {}
+    default = _ffi.get_option("qr_blocked")
+    try:
+        for v in (0, 1):
+            _ffi.set_option("qr_blocked", v)
+            qr = a0.copy()
+            out[v] = (qr, lair.lapack.geqrf(qr))
+    finally:
+        _ffi.set_option("qr_blocked", default)
+    eps = np.finfo(dt).eps
+    scale = np.max(np.abs(out[0][0]))
+    assert np.max(np.abs(out[0][0] - out[1][0])) <= 100 * eps * max(shape) * scale
+    assert np.max(np.abs(out[0][1] - out[1][1])) <= 100 * eps * max(shape)
+    if shape[0] <= 1000:
+        ref = a0.copy()
+        tau_o = oracle.geqrf(ref)
+        assert np.max(np.abs(out[1][0] - ref)) <= 100 * eps * max(shape) * scale
+        q = lair.lapack.qr_q(out[1][0], out[1][1])
+        fact, orth = qr_errors(a0, q, np.triu(out[1][0]))
+        fact_o, orth_o = qr_errors(a0, oracle.qr_q(ref, tau_o), np.triu(ref))
+        assert fact <= 10 * max(fact_o, 0.01) and orth <= 10 * max(orth_o, 0.01), (fact, fact_o, orth, orth_o)

@@ -406,6 +406,29 @@ def sec_cxgetrf():
         _ffi.set_option("cx_blocked", 1)
 
 
+def sec_qr():
+    """geqrf device-resident (qr.cu / qr_blocked.cu): time, factorization error ||A - QR|| via R^T R = A^T A surrogate-free
+    check on a few columns is too weak, so Q is applied implicitly: ||Q^T A - R|| is not available without Q; we report
+    the Gram identity ||R^T R - A^T A|| / (n eps ||A||^2), which holds iff R is the R factor of A up to signs."""
+    for dt, pfx in ((torch.float64, "d"), (torch.float32, "s")):
+        fn = getattr(L, f"lair_b200_{pfx}geqrf_dev")
+        for (m, n), modes in (((1024, 1024), (1, 0)), ((2048, 2048), (1, 0)), ((4096, 4096), (1,)), ((8192, 8192), (1,)), ((65536, 256), (1, 0))):
+            for blocked in modes:
+                _ffi.set_option("qr_blocked", blocked)
+                a0 = torch.rand(m, n, dtype=dt, device="cuda") * 10
+                a = a0.clone()
+                tau = torch.empty(min(m, n), dtype=dt, device="cuda")
+                best, med = timeit(lambda: _ffi.check(fn(m, n, a.data_ptr(), n, tau.data_ptr(), stream())),
+                                   reps=2, warm=1, setup=lambda: a.copy_(a0))
+                r = torch.triu(a[:n, :]).double()
+                a64 = a0.double()
+                eps = (2.0 ** -53) if dt == torch.float64 else (2.0 ** -24)
+                gram = float(torch.linalg.norm(r.T @ r - a64.T @ a64) / (max(m, n) * eps * torch.linalg.norm(a64) ** 2))
+                flops = 2.0 * m * n * n - 2.0 / 3.0 * n ** 3
+                out(bench=f"{pfx}geqrf", m=m, n=n, blocked=blocked, ms_best=best, ms_med=med, tflops=flops / best * 1e-9, gram_error=gram)
+        _ffi.set_option("qr_blocked", 1)
+
+
 def sec_tune8192():
     """dgetrf n = 8192: sweep of the sweep's own thresholds (block-width switch, where the chain moves to the panel stream)."""
     fn = L.lair_b200_dgetrf_dev
