@@ -8,8 +8,9 @@
 //      (two cluster barriers per column).  The same dot products against the columns LEFT of j are V^T v_j, from which
 //      the kernel builds the triangular factor T (larft's forward / columnwise recurrence, src/lapack/larft.rs) on the fly.
 //   2. pack: Vp = V with its unit diagonal and zeros above (rows x 32), NVt = -V^T (32 x rows).
-//   3. trailing update C := (I - V T^T V^T) C as three products on the DMMA / FFMA GEMM kernels (gemm_minus_dev: C -= A B):
-//      W = V^T C  (W = 0; W -= NVt C),  W := T^T W (32-row triangle, one small kernel),  C -= Vp W.
+//   3. trailing update C := (I - V T^T V^T) C:  W = V^T C by a split-row SIMT kernel (a reduction over the rows: partial
+//      products per 512-row chunk, summed in order inside the next kernel),  W := T^T W (32-row triangle),  C -= Vp W on
+//      the DMMA / FFMA GEMM kernel of the LU path (gemm_minus_dev).
 // tau, R and the reflectors come out in the reference's (LAPACK's) storage; results agree with the unblocked loop to
 // rounding (tests/test_gpu_qr.py: blocked vs unblocked vs oracle).
 #include <cooperative_groups.h>
@@ -216,10 +217,77 @@ __global__ void qr_pack_kernel(const R* __restrict__ A, long long lda, int rows,
     }
 }
 
-// W (QB x ncols, ld ldw) := T^T W, T upper triangular QB x QB (row-major ld QB)
+// Partial products of W = V^T C: CTA (x, y) takes 128 columns of C and the row chunk y (VT_RC rows) and writes the
+// 32 x 128 partial sum to Wp[y] (ld ldw).  A reduction over the rows is badly served by an output-tiled GEMM (M = 32,
+// K = rows: 5 TFLOP/s on the DMMA kernel), so this is a SIMT kernel with 4 x 8 register tiles: per staged row 6 shared
+// loads feed 32 FMAs, and the (column tile) x (row chunk) grid fills the GPU even for narrow trailing blocks.
+// The partials are summed in chunk order by qr_trmm_tt_kernel: deterministic, no atomics.
+constexpr int VT_BN = 128, VT_RC = 512, VT_KS = 16, VT_THREADS = 128;
+// column j (0..7) of thread tj (0..15) inside the 128-column tile: 16-byte groups interleaved across the threads, so a
+// quarter-warp's 16-byte shared loads fall in distinct banks (8 consecutive columns per thread would be 4-way conflicted)
+template <class R>
+__device__ __forceinline__ constexpr int vt_col(int tj, int j) {
+    constexpr int VEC = 16 / (int)sizeof(R);
+    return (j / VEC) * (16 * VEC) + tj * VEC + (j % VEC);
+}
+template <class R>
+__global__ void __launch_bounds__(VT_THREADS)
+qr_vtc_kernel(const R* __restrict__ Vp /* rows x QB */, const R* __restrict__ Cm, long long ldc, int rows, int ncols,
+              R* __restrict__ Wp, long long ldw, long long part_stride) {
+    __shared__ __align__(16) R Vs[VT_KS][QB];
+    __shared__ __align__(16) R Cs[VT_KS][VT_BN];
+    const int tid = threadIdx.x;
+    const int ti = tid / 16, tj = tid % 16;  // V columns 4 ti .. +4, C columns 8 tj .. +8
+    const int c0 = blockIdx.x * VT_BN;
+    const int r0 = blockIdx.y * VT_RC;
+    const int rend = min(rows, r0 + VT_RC);
+    R acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = R(0);
+    for (int rb = r0; rb < rend; rb += VT_KS) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < VT_KS * QB / VT_THREADS; ++q) {
+            const int idx = tid + q * VT_THREADS;
+            const int r = idx / QB, k = idx % QB;
+            Vs[r][k] = (rb + r < rend) ? Vp[(long long)(rb + r) * QB + k] : R(0);
+        }
+#pragma unroll
+        for (int q = 0; q < VT_KS * VT_BN / VT_THREADS; ++q) {
+            const int idx = tid + q * VT_THREADS;
+            const int r = idx / VT_BN, c = idx % VT_BN;
+            Cs[r][c] = (rb + r < rend && c0 + c < ncols) ? Cm[(long long)(rb + r) * ldc + c0 + c] : R(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < VT_KS; ++r) {
+            R v[4], c[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = Vs[r][ti * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = Cs[r][vt_col<R>(tj, j)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(v[i], c[j], acc[i][j]);
+        }
+    }
+    R* out = Wp + (long long)blockIdx.y * part_stride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + vt_col<R>(tj, j);
+            if (c < ncols) out[(long long)(ti * 4 + i) * ldw + c] = acc[i][j];
+        }
+}
+
+// W (QB x ncols, ld ldw) := T^T (sum of the nparts partial products Wp[p]), T upper triangular QB x QB (row-major ld QB)
 template <class R>
 __global__ void __launch_bounds__(128)
-qr_trmm_tt_kernel(const R* __restrict__ T, R* __restrict__ W, long long ldw, int ncols) {
+qr_trmm_tt_kernel(const R* __restrict__ T, const R* __restrict__ Wp, long long part_stride, int nparts, R* __restrict__ W, long long ldw, int ncols) {
     __shared__ R Ts[QB][QB + 1];
     for (int idx = threadIdx.x; idx < QB * QB; idx += 128) Ts[idx / QB][idx % QB] = T[idx];
     __syncthreads();
@@ -227,7 +295,12 @@ qr_trmm_tt_kernel(const R* __restrict__ T, R* __restrict__ W, long long ldw, int
     if (c >= ncols) return;
     R wv[QB];
 #pragma unroll
-    for (int k = 0; k < QB; ++k) wv[k] = W[(long long)k * ldw + c];
+    for (int k = 0; k < QB; ++k) wv[k] = R(0);
+    for (int p = 0; p < nparts; ++p) {
+        const R* src = Wp + (long long)p * part_stride;
+#pragma unroll
+        for (int k = 0; k < QB; ++k) wv[k] += src[(long long)k * ldw + c];
+    }
 #pragma unroll
     for (int i = QB - 1; i >= 0; --i) {
         R s = R(0);
@@ -312,10 +385,12 @@ template <class R>
 int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaStream_t s) {
     const int64_t k = m < n ? m : n;
     if (k == 0) return LAIR_B200_OK;
-    // workspace: T (QB x QB) | Vp (m x QB) | NVt (QB x ldt) | W (QB x n)
+    // workspace: T (2 x QB x QB) | Vp (m x QB) | NVt (QB x ldt, unused by the default path) | W (QB x n) | Wp (nparts x QB x n)
     const int64_t ldt = (m + 3) / 4 * 4, ldw = (n + 3) / 4 * 4;
+    const int64_t max_parts = (m + VT_RC - 1) / VT_RC;
     const size_t off_T = 0, off_V = 4096 * sizeof(R), off_N = off_V + (size_t)m * QB * sizeof(R), off_W = off_N + (size_t)QB * ldt * sizeof(R);
-    const size_t total = off_W + (size_t)QB * ldw * sizeof(R);
+    const size_t off_P = off_W + (size_t)QB * ldw * sizeof(R);
+    const size_t total = off_P + (size_t)max_parts * QB * ldw * sizeof(R);
     {   // capacity check before anything is modified
         const size_t limit = ctx().smem_optin > 20480 ? ctx().smem_optin - 20480 : 0;
         const int64_t cap = (int64_t)(limit / (QLD * sizeof(R)));
@@ -323,31 +398,75 @@ int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaS
     }
     void* ws = nullptr;
     LAIR_CHECK(qr_workspace(total, &ws, s));
-    R* dT = reinterpret_cast<R*>((char*)ws + off_T);
+    R* dT[2] = {reinterpret_cast<R*>((char*)ws + off_T), reinterpret_cast<R*>((char*)ws + off_T) + 2048};
     R* dV = reinterpret_cast<R*>((char*)ws + off_V);
     R* dN = reinterpret_cast<R*>((char*)ws + off_N);
     R* dW = reinterpret_cast<R*>((char*)ws + off_W);
-    for (int64_t j0 = 0; j0 < k; j0 += QB) {
+    R* dP = reinterpret_cast<R*>((char*)ws + off_P);
+    const long long part_stride = (long long)QB * ldw;
+    // One block of lookahead, as in the LU sweep (blocked.cu): the panel of block b+1 (stream P, high priority, one
+    // cluster = 16 SMs) runs under the bulk of block b's trailing update (stream M).
+    //   M: wait panel(b) | pack | update(next block's columns) -> EN | update(rest)
+    //   P: wait EN | panel(b+1) -> EP
+    // P only touches the next block's columns, its tau range and the other T buffer.
+    const bool look = ctx().opt.lookahead != 0 && k > QB;
+    cudaStream_t M = s, P = look ? ctx().aux_stream : s;
+    cudaEvent_t EP = ctx().ev[0], EN = ctx().ev[1];
+    auto panel = [&](int64_t j0, int64_t jb, int buf, cudaStream_t st) -> int {
+        const int rc = qr_panel_dev<R>(m - j0, jb, d_a + j0 * lda + j0, lda, d_tau + j0, dT[buf], st);
+        if (rc == LAIR_B200_ERR_UNSUPPORTED) {
+            set_error("geqrf: panel of %lld rows does not fit one cluster", (long long)(m - j0));
+            return LAIR_B200_ERR_CUDA;
+        }
+        return rc;
+    };
+    // C (rows x ncols at c) := (I - V T^T V^T) C with the packed reflectors of the current block
+    auto update = [&](int64_t rows, R* c, int64_t ncols, const R* T) -> int {
+        if (ncols <= 0) return LAIR_B200_OK;
+        const int nparts = (int)((rows + VT_RC - 1) / VT_RC);
+        {   // W = V^T C as partial products over row chunks, summed inside the T^T kernel
+            ProfScope prof(kProfTrsm, M, 2.0 * QB * (double)ncols * (double)rows);
+            dim3 grid((unsigned)((ncols + VT_BN - 1) / VT_BN), (unsigned)nparts);
+            qr_vtc_kernel<R><<<grid, VT_THREADS, 0, M>>>(dV, c, (long long)lda, (int)rows, (int)ncols, dP, (long long)ldw, part_stride);
+            LAIR_LAUNCH_CHECK();
+        }
+        qr_trmm_tt_kernel<R><<<(unsigned)((ncols + 127) / 128), 128, 0, M>>>(T, dP, part_stride, nparts, dW, (long long)ldw, (int)ncols);  // W := T^T W
+        LAIR_LAUNCH_CHECK();
+        return gemm_minus_dev<R>(rows, ncols, QB, dV, QB, dW, ldw, c, lda, M);              // C -= V W
+    };
+    if (look) {
+        LAIR_CUDA_CHECK(cudaEventRecord(EN, M));  // P starts after everything already queued on the caller's stream
+        LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+    }
+    LAIR_CHECK(panel(0, k < QB ? k : QB, 0, P));
+    int buf = 0;
+    for (int64_t j0 = 0; j0 < k; j0 += QB, buf ^= 1) {
         const int64_t jb = (k - j0) < QB ? (k - j0) : QB;
         const int64_t rows = m - j0;
         R* ajj = d_a + j0 * lda + j0;
-        // the panel may be wider than jb when the matrix is wide and this is the last block: only jb reflectors exist
-        const int rc = qr_panel_dev<R>(rows, jb, ajj, lda, d_tau + j0, dT, s);
-        if (rc != LAIR_B200_OK) {
-            if (rc == LAIR_B200_ERR_UNSUPPORTED) set_error("geqrf: panel of %lld rows does not fit one cluster", (long long)rows);
-            return rc == LAIR_B200_ERR_UNSUPPORTED ? LAIR_B200_ERR_CUDA : rc;
+        const int64_t c0 = j0 + jb;                                  // first column right of the block
+        const int64_t nb2 = c0 < k ? ((k - c0) < QB ? (k - c0) : QB) : 0;  // width of the next block
+        if (look) {
+            LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
+            LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
         }
-        const int64_t nc = n - j0 - jb;
-        if (nc <= 0) continue;
+        if (c0 >= n) break;
         const unsigned pb = (unsigned)std::min<int64_t>((rows * QB + 255) / 256, (int64_t)ctx().sm_count * 8);
-        qr_pack_kernel<R><<<pb, 256, 0, s>>>(ajj, (long long)lda, (int)rows, (int)jb, dV, dN, (long long)ldt);
+        qr_pack_kernel<R><<<pb, 256, 0, M>>>(ajj, (long long)lda, (int)rows, (int)jb, dV, dN, (long long)ldt);
         LAIR_LAUNCH_CHECK();
-        LAIR_CUDA_CHECK(cudaMemsetAsync(dW, 0, (size_t)QB * ldw * sizeof(R), s));
-        R* c = ajj + jb;
-        LAIR_CHECK(gemm_minus_dev<R>(QB, nc, rows, dN, ldt, c, lda, dW, ldw, s));       // W = V^T C
-        qr_trmm_tt_kernel<R><<<(unsigned)((nc + 127) / 128), 128, 0, s>>>(dT, dW, (long long)ldw, (int)nc);  // W := T^T W
-        LAIR_LAUNCH_CHECK();
-        LAIR_CHECK(gemm_minus_dev<R>(rows, nc, QB, dV, QB, dW, ldw, c, lda, s));        // C -= V W
+        if (nb2 > 0) {
+            LAIR_CHECK(update(rows, ajj + jb, nb2, dT[buf]));        // the next block's columns first ...
+            if (look) {
+                LAIR_CUDA_CHECK(cudaEventRecord(EN, M));
+                LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+            }
+            LAIR_CHECK(panel(c0, nb2, buf ^ 1, P));                   // ... so its panel can start under the rest
+        }
+        LAIR_CHECK(update(rows, ajj + jb + nb2, n - c0 - nb2, dT[buf]));
+    }
+    if (look) {  // the caller's stream sees the last panel too
+        LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
+        LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
     }
     return LAIR_B200_OK;
 }
