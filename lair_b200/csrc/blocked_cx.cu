@@ -63,9 +63,10 @@ struct PackBuf {
     void* p = nullptr;
     size_t bytes = 0;
 };
-// grow-only device buffers of the packed operands (one pair per process; every use is ordered on the caller's stream)
+// grow-only device buffers of the packed operands (one pair per stream role; every use is ordered on its stream)
 int pack_buffers(size_t a_bytes, size_t b_bytes, void** pa, void** pb, cudaStream_t s) {
-    static PackBuf bufs[2];
+    static PackBuf all[2][2];  // [0]: the caller's stream, [1]: the lookahead stream -- the two run concurrently
+    PackBuf* bufs = all[s == ctx().aux_stream ? 1 : 0];
     const size_t want[2] = {a_bytes, b_bytes};
     for (int i = 0; i < 2; ++i) {
         if (bufs[i].bytes < want[i]) {
@@ -216,52 +217,85 @@ struct FactorCx {
     cudaStream_t s;
 
     T* at(int64_t r, int64_t c) const { return A + r * lda + c; }
-    int swap_cols(int64_t c0, int64_t c1, int64_t k0, int64_t k1) const {
+    int swap_cols(int64_t c0, int64_t c1, int64_t k0, int64_t k1, cudaStream_t st) const {
         if (c1 <= c0 || k1 <= k0) return LAIR_B200_OK;
-        return laswp_cx(c1 - c0, A + c0, lda, k0, k1, ipiv, s);
+        return laswp_cx(c1 - c0, A + c0, lda, k0, k1, ipiv, st);
     }
     // factor columns [j0, j0 + w) on rows j0..m; pivots land in ipiv[j0 .. j0 + min(w, m - j0))
-    int rec(int64_t j0, int64_t w) const {
+    int rec(int64_t j0, int64_t w, cudaStream_t st) const {
         const int64_t rows = m - j0;
         if (rows <= 0 || w <= 0) return LAIR_B200_OK;
         if (w <= kLeaf) {
             if (ctx().opt.cx_blocked == 1) {  // one cluster, the panel in shared memory (panel_cx.cu)
-                const int rc = panel_cx_dev<T>(rows, w, at(j0, j0), lda, ipiv + j0, (int32_t)j0, info, std_layout, s);
+                const int rc = panel_cx_dev<T>(rows, w, at(j0, j0), lda, ipiv + j0, (int32_t)j0, info, std_layout, st);
                 if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
             }
-            return getrf_small_dev<T>(rows, w, at(j0, j0), lda, ipiv + j0, info, std_layout, s, (int32_t)j0, true);
+            return getrf_small_dev<T>(rows, w, at(j0, j0), lda, ipiv + j0, info, std_layout, st, (int32_t)j0, true);
         }
         int64_t w1 = (w / 2 + kLeaf - 1) / kLeaf * kLeaf;
         if (w1 >= w) w1 = w - kLeaf;
-        LAIR_CHECK(rec(j0, w1));
+        LAIR_CHECK(rec(j0, w1, st));
         const int64_t kd = w1 < rows ? w1 : rows;  // pivots produced by the left half
         const int64_t r1 = j0 + kd, c1 = j0 + w1, w2 = w - w1;
-        LAIR_CHECK(swap_cols(c1, c1 + w2, j0, r1));                                               // laswp (getrf.rs:270-277)
-        LAIR_CHECK(trsm_lower_unit_cx<T>(kd, w2, at(j0, j0), lda, at(j0, c1), lda, s));            // trsm  (:278-283)
+        LAIR_CHECK(swap_cols(c1, c1 + w2, j0, r1, st));                                           // laswp (getrf.rs:270-277)
+        LAIR_CHECK(trsm_lower_unit_cx<T>(kd, w2, at(j0, j0), lda, at(j0, c1), lda, st));           // trsm  (:278-283)
         if (m > r1 && kd == w1) {
-            LAIR_CHECK(gemm_minus_cx<T>(m - r1, w2, w1, at(r1, j0), lda, at(j0, c1), lda, at(r1, c1), lda, s));  // gemm (:289-296)
-            LAIR_CHECK(rec(r1, w2));                                                                 // recurse (:297); r1 == c1
+            LAIR_CHECK(gemm_minus_cx<T>(m - r1, w2, w1, at(r1, j0), lda, at(j0, c1), lda, at(r1, c1), lda, st));  // gemm (:289-296)
+            LAIR_CHECK(rec(r1, w2, st));                                                             // recurse (:297); r1 == c1
             const int64_t kd2 = (m - r1) < w2 ? (m - r1) : w2;
-            LAIR_CHECK(swap_cols(j0, c1, r1, r1 + kd2));                                            // laswp left (:308-315)
+            LAIR_CHECK(swap_cols(j0, c1, r1, r1 + kd2, st));                                        // laswp left (:308-315)
         }
         return LAIR_B200_OK;
     }
+    // trailing update of columns [c0, c1) with the factored block [j0, j0 + jb)
+    int update(int64_t j0, int64_t jb, int64_t c0, int64_t c1, cudaStream_t st) const {
+        if (c1 <= c0) return LAIR_B200_OK;
+        const int64_t r1 = j0 + jb;
+        LAIR_CHECK(swap_cols(c0, c1, j0, r1, st));
+        LAIR_CHECK(trsm_lower_unit_cx<T>(jb, c1 - c0, at(j0, j0), lda, at(j0, c0), lda, st));
+        if (r1 < m) LAIR_CHECK(gemm_minus_cx<T>(m - r1, c1 - c0, jb, at(r1, j0), lda, at(j0, c0), lda, at(r1, c0), lda, st));
+        return LAIR_B200_OK;
+    }
 
+    // Right-looking sweep with one block of lookahead, as blocked.cu: the panel recursion of block b+1 (stream P, high
+    // priority) runs under the bulk of block b's trailing update (stream M).  The two streams touch disjoint column and
+    // ipiv ranges; each has its own packed-operand buffers (pack_buffers).
     int run() const {
         const int64_t kmin = m < n ? m : n;
         set_info_kernel<<<1, 1, 0, s>>>(info, -1);
         LAIR_LAUNCH_CHECK();
         const int64_t nb = 128;
+        auto width = [&](int64_t j) { return (kmin - j) < nb ? (kmin - j) : nb; };
+        const bool look = ctx().opt.lookahead != 0 && kmin > nb;
+        cudaStream_t M = s, P = look ? ctx().aux_stream : s;
+        cudaEvent_t EP = ctx().ev[0], EN = ctx().ev[1];
+        if (look) {
+            LAIR_CUDA_CHECK(cudaEventRecord(EN, M));  // P starts after everything already queued on the caller's stream
+            LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+        }
+        LAIR_CHECK(rec(0, width(0), P));
         for (int64_t j0 = 0; j0 < kmin; j0 += nb) {
-            const int64_t jb = (kmin - j0) < nb ? (kmin - j0) : nb;
-            LAIR_CHECK(rec(j0, jb));
+            const int64_t jb = width(j0);
             const int64_t c0 = j0 + jb;
-            LAIR_CHECK(swap_cols(0, j0, j0, c0));   // interchanges reach back into L
-            if (c0 < n) {
-                LAIR_CHECK(swap_cols(c0, n, j0, c0));
-                LAIR_CHECK(trsm_lower_unit_cx<T>(jb, n - c0, at(j0, j0), lda, at(j0, c0), lda, s));
-                if (c0 < m) LAIR_CHECK(gemm_minus_cx<T>(m - c0, n - c0, jb, at(c0, j0), lda, at(j0, c0), lda, at(c0, c0), lda, s));
+            const int64_t nb2 = c0 < kmin ? width(c0) : 0;
+            if (look) {
+                LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
+                LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
             }
+            if (nb2 > 0) {
+                LAIR_CHECK(update(j0, jb, c0, c0 + nb2, M));   // the next block's columns first ...
+                if (look) {
+                    LAIR_CUDA_CHECK(cudaEventRecord(EN, M));
+                    LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+                }
+                LAIR_CHECK(rec(c0, nb2, P));                    // ... so its panel recursion starts under the rest
+            }
+            LAIR_CHECK(update(j0, jb, c0 + nb2, n, M));
+            LAIR_CHECK(swap_cols(0, j0, j0, c0, M));            // interchanges reach back into L (off the critical path)
+        }
+        if (look) {
+            LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
+            LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
         }
         return LAIR_B200_OK;
     }
