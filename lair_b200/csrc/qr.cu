@@ -225,6 +225,9 @@ int qr_q_dev(int64_t m, int64_t n, const T* d_qr, int64_t ldqr, const T* d_tau, 
     LAIR_REQUIRE(m >= 0 && n >= 0 && ldqr >= n && ldq >= m, "qr_q: bad shape");
     if (m == 0) return LAIR_B200_OK;
     const int64_t k = m < n ? m : n;
+    if constexpr (!Ops<T>::is_complex) {
+        if (ctx().opt.qr_blocked != 0 && k >= 64) return qr_q_blocked_dev<T>(m, n, d_qr, ldqr, d_tau, d_q, ldq, s);
+    }
     const unsigned blocks = (unsigned)std::min<int64_t>((m * m + 255) / 256, (int64_t)ctx().sm_count * 8);
     q_init_kernel<T><<<blocks, 256, 0, s>>>(d_qr, (long long)ldqr, (int)m, (int)k, d_q, (long long)ldq);
     LAIR_LAUNCH_CHECK();

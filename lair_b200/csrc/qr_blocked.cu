@@ -285,7 +285,7 @@ qr_vtc_kernel(const R* __restrict__ Vp /* rows x QB */, const R* __restrict__ Cm
 }
 
 // W (QB x ncols, ld ldw) := T^T (sum of the nparts partial products Wp[p]), T upper triangular QB x QB (row-major ld QB)
-template <class R>
+template <class R, bool TRANS = true>
 __global__ void __launch_bounds__(128)
 qr_trmm_tt_kernel(const R* __restrict__ T, const R* __restrict__ Wp, long long part_stride, int nparts, R* __restrict__ W, long long ldw, int ncols) {
     __shared__ R Ts[QB][QB + 1];
@@ -304,10 +304,41 @@ qr_trmm_tt_kernel(const R* __restrict__ T, const R* __restrict__ Wp, long long p
 #pragma unroll
     for (int i = QB - 1; i >= 0; --i) {
         R s = R(0);
+        if constexpr (TRANS) {  // (T^T w)[i] = sum_{k <= i} T[k][i] w[k]
 #pragma unroll
-        for (int k = 0; k <= i; ++k) s += Ts[k][i] * wv[k];
+            for (int k = 0; k <= i; ++k) s += Ts[k][i] * wv[k];
+        } else {                // (T w)[i] = sum_{k >= i} T[i][k] w[k]   (accumulating Q = H_0 H_1 ... applies T itself)
+#pragma unroll
+            for (int k = i; k < QB; ++k) s += Ts[i][k] * wv[k];
+        }
         W[(long long)i * ldw + c] = s;
     }
+}
+
+// T (QB x QB, row-major) from tau and the Gram matrix G = V^T V, given as nparts partial products (32 x 32, ld QB each):
+// T[j][j] = tau_j, T[0..j, j] = -tau_j T[0..j, 0..j] G[0..j, j]  (larft, forward columnwise; src/lapack/larft.rs).
+template <class R>
+__global__ void __launch_bounds__(QB * QB)
+qr_build_t_kernel(const R* __restrict__ Gp, long long part_stride, int nparts, const R* __restrict__ tau, int w, R* __restrict__ T) {
+    __shared__ R G[QB][QB + 1];
+    __shared__ R Ts[QB][QB + 1];
+    const int i = threadIdx.x / QB, k = threadIdx.x % QB;
+    R g = R(0);
+    for (int p = 0; p < nparts; ++p) g += Gp[(long long)p * part_stride + i * QB + k];
+    G[i][k] = g;
+    Ts[i][k] = R(0);
+    __syncthreads();
+    for (int j = 0; j < w; ++j) {
+        const R t = tau[j];
+        if (i == 0 && k < j) {  // row k of column j
+            R s = R(0);
+            for (int q = k; q < j; ++q) s += Ts[k][q] * G[q][j];
+            Ts[k][j] = -t * s;
+        }
+        if (i == 0 && k == j) Ts[j][j] = t;
+        __syncthreads();
+    }
+    T[i * QB + k] = Ts[i][k];
 }
 
 struct QrWork {
@@ -470,6 +501,68 @@ int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaS
     }
     return LAIR_B200_OK;
 }
+// qr::Factorized::q (qr.rs:27-59) by blocks: Q = H_0 H_1 ... H_{k-1} applied to the identity from the last block
+// backwards, each block as I - V T V^T on the trailing square (the standard blocked ungqr; same Q to rounding as the
+// reference's reflector-at-a-time loop).  T is rebuilt per block from tau and V^T V (split-row kernel + larft recurrence).
+template <class R>
+__global__ void q_identity_kernel(R* __restrict__ Q, long long ldq, int m) {
+    const long long total = (long long)m * m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / m), c = (int)(idx - (long long)r * m);
+        Q[(long long)r * ldq + c] = r == c ? R(1) : R(0);
+    }
+}
+
+template <class R>
+int qr_q_blocked_dev(int64_t m, int64_t n, const R* d_qr, int64_t ldqr, const R* d_tau, R* d_q, int64_t ldq, cudaStream_t s) {
+    const int64_t k = m < n ? m : n;
+    const int64_t ldw = (m + 3) / 4 * 4;
+    const int64_t max_parts = (m + VT_RC - 1) / VT_RC;
+    // workspace: T | Vp (m x QB) | W (QB x m) | Wp (parts x QB x m)
+    const size_t off_T = 0, off_V = 4096 * sizeof(R), off_W = off_V + (size_t)m * QB * sizeof(R);
+    const size_t off_P = off_W + (size_t)QB * ldw * sizeof(R);
+    const size_t total = off_P + (size_t)max_parts * QB * ldw * sizeof(R);
+    void* ws = nullptr;
+    LAIR_CHECK(qr_workspace(total, &ws, s));
+    R* dT = reinterpret_cast<R*>((char*)ws + off_T);
+    R* dV = reinterpret_cast<R*>((char*)ws + off_V);
+    R* dW = reinterpret_cast<R*>((char*)ws + off_W);
+    R* dP = reinterpret_cast<R*>((char*)ws + off_P);
+    R* dN = dP;  // qr_pack_kernel also writes -V^T; it is not needed here and lands in the partial buffer before it is used
+    const unsigned ib = (unsigned)std::min<int64_t>((m * m + 255) / 256, (int64_t)ctx().sm_count * 8);
+    q_identity_kernel<R><<<ib, 256, 0, s>>>(d_q, (long long)ldq, (int)m);
+    LAIR_LAUNCH_CHECK();
+    const int64_t nblocks = (k + QB - 1) / QB;
+    for (int64_t b = nblocks - 1; b >= 0; --b) {
+        const int64_t j0 = b * QB;
+        const int64_t jb = (k - j0) < QB ? (k - j0) : QB;
+        const int64_t rows = m - j0, nc = m - j0;
+        const int nparts = (int)((rows + VT_RC - 1) / VT_RC);
+        const unsigned pb = (unsigned)std::min<int64_t>((rows * QB + 255) / 256, (int64_t)ctx().sm_count * 8);
+        qr_pack_kernel<R><<<pb, 256, 0, s>>>(d_qr + j0 * ldqr + j0, (long long)ldqr, (int)rows, (int)jb, dV, dN, (long long)rows);
+        LAIR_LAUNCH_CHECK();
+        // T from tau and V^T V
+        qr_vtc_kernel<R><<<dim3(1, (unsigned)nparts), VT_THREADS, 0, s>>>(dV, dV, (long long)QB, (int)rows, QB, dP, (long long)QB, (long long)QB * QB);
+        LAIR_LAUNCH_CHECK();
+        qr_build_t_kernel<R><<<1, QB * QB, 0, s>>>(dP, (long long)QB * QB, nparts, d_tau + j0, (int)jb, dT);
+        LAIR_LAUNCH_CHECK();
+        // Q_sub := (I - V T V^T) Q_sub
+        R* qs = d_q + j0 * ldq + j0;
+        {
+            ProfScope prof(kProfTrsm, s, 2.0 * QB * (double)nc * (double)rows);
+            qr_vtc_kernel<R><<<dim3((unsigned)((nc + VT_BN - 1) / VT_BN), (unsigned)nparts), VT_THREADS, 0, s>>>(dV, qs, (long long)ldq, (int)rows, (int)nc, dP, (long long)ldw,
+                                                                                                            (long long)QB * ldw);
+            LAIR_LAUNCH_CHECK();
+        }
+        qr_trmm_tt_kernel<R, false><<<(unsigned)((nc + 127) / 128), 128, 0, s>>>(dT, dP, (long long)QB * ldw, nparts, dW, (long long)ldw, (int)nc);
+        LAIR_LAUNCH_CHECK();
+        LAIR_CHECK(gemm_minus_dev<R>(rows, nc, QB, dV, QB, dW, ldw, qs, ldq, s));
+    }
+    return LAIR_B200_OK;
+}
+template int qr_q_blocked_dev<float>(int64_t, int64_t, const float*, int64_t, const float*, float*, int64_t, cudaStream_t);
+template int qr_q_blocked_dev<double>(int64_t, int64_t, const double*, int64_t, const double*, double*, int64_t, cudaStream_t);
+
 template int geqrf_blocked_dev<float>(int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
 template int geqrf_blocked_dev<double>(int64_t, int64_t, double*, int64_t, double*, cudaStream_t);
 
