@@ -233,14 +233,14 @@ __device__ __forceinline__ constexpr int vt_col(int tj, int j) {
 template <class R>
 __global__ void __launch_bounds__(VT_THREADS)
 qr_vtc_kernel(const R* __restrict__ Vp /* rows x QB */, const R* __restrict__ Cm, long long ldc, int rows, int ncols,
-              R* __restrict__ Wp, long long ldw, long long part_stride) {
+              R* __restrict__ Wp, long long ldw, long long part_stride, int rc = VT_RC) {
     __shared__ __align__(16) R Vs[VT_KS][QB];
     __shared__ __align__(16) R Cs[VT_KS][VT_BN];
     const int tid = threadIdx.x;
     const int ti = tid / 16, tj = tid % 16;  // V columns 4 ti .. +4, C columns 8 tj .. +8
     const int c0 = blockIdx.x * VT_BN;
-    const int r0 = blockIdx.y * VT_RC;
-    const int rend = min(rows, r0 + VT_RC);
+    const int r0 = blockIdx.y * rc;
+    const int rend = min(rows, r0 + rc);
     R acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -284,32 +284,41 @@ qr_vtc_kernel(const R* __restrict__ Vp /* rows x QB */, const R* __restrict__ Cm
         }
 }
 
-// W (QB x ncols, ld ldw) := T^T (sum of the nparts partial products Wp[p]), T upper triangular QB x QB (row-major ld QB)
+// W (QB x ncols, ld ldw) := T^T (sum of the nparts partial products Wp[p], ld ldp), T upper triangular QB x QB (row-major ld QB)
 template <class R, bool TRANS = true>
 __global__ void __launch_bounds__(128)
-qr_trmm_tt_kernel(const R* __restrict__ T, const R* __restrict__ Wp, long long part_stride, int nparts, R* __restrict__ W, long long ldw, int ncols) {
+qr_trmm_tt_kernel(const R* __restrict__ T, const R* __restrict__ Wp, long long part_stride, long long ldp, int nparts, R* __restrict__ W, long long ldw,
+                  int ncols) {
+    // CTA = 32 columns x 4 groups of 8 rows: thread (c, g) sums the partial products of rows 8g .. 8g+8 of its column (in
+    // chunk order), the sums meet in shared memory, then the same thread forms 8 rows of the triangular product.
     __shared__ R Ts[QB][QB + 1];
+    __shared__ R ws[QB][QB + 1];
     for (int idx = threadIdx.x; idx < QB * QB; idx += 128) Ts[idx / QB][idx % QB] = T[idx];
-    __syncthreads();
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= ncols) return;
-    R wv[QB];
+    const int cl = threadIdx.x % QB, g = threadIdx.x / QB;
+    const int c = blockIdx.x * QB + cl;
+    R acc[8];
 #pragma unroll
-    for (int k = 0; k < QB; ++k) wv[k] = R(0);
-    for (int p = 0; p < nparts; ++p) {
-        const R* src = Wp + (long long)p * part_stride;
+    for (int q = 0; q < 8; ++q) acc[q] = R(0);
+    if (c < ncols) {
+#pragma unroll 4
+        for (int p = 0; p < nparts; ++p) {
+            const R* src = Wp + (long long)p * part_stride + (long long)(8 * g) * ldp + c;
 #pragma unroll
-        for (int k = 0; k < QB; ++k) wv[k] += src[(long long)k * ldw + c];
+            for (int q = 0; q < 8; ++q) acc[q] += src[(long long)q * ldp];
+        }
     }
 #pragma unroll
-    for (int i = QB - 1; i >= 0; --i) {
+    for (int q = 0; q < 8; ++q) ws[8 * g + q][cl] = acc[q];
+    __syncthreads();
+    if (c >= ncols) return;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int i = 8 * g + q;
         R s = R(0);
         if constexpr (TRANS) {  // (T^T w)[i] = sum_{k <= i} T[k][i] w[k]
-#pragma unroll
-            for (int k = 0; k <= i; ++k) s += Ts[k][i] * wv[k];
+            for (int k = 0; k <= i; ++k) s += Ts[k][i] * ws[k][cl];
         } else {                // (T w)[i] = sum_{k >= i} T[i][k] w[k]   (accumulating Q = H_0 H_1 ... applies T itself)
-#pragma unroll
-            for (int k = i; k < QB; ++k) s += Ts[i][k] * wv[k];
+            for (int k = i; k < QB; ++k) s += Ts[i][k] * ws[k][cl];
         }
         W[(long long)i * ldw + c] = s;
     }
@@ -421,7 +430,8 @@ int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaS
     const int64_t max_parts = (m + VT_RC - 1) / VT_RC;
     const size_t off_T = 0, off_V = 4096 * sizeof(R), off_N = off_V + (size_t)m * QB * sizeof(R), off_W = off_N + (size_t)QB * ldt * sizeof(R);
     const size_t off_P = off_W + (size_t)QB * ldw * sizeof(R);
-    const size_t total = off_P + (size_t)max_parts * QB * ldw * sizeof(R);
+    const size_t narrow_parts = (size_t)((m + 127) / 128) * QB * QB;  // the lookahead's narrow updates: 128-row chunks, 32 columns
+    const size_t total = off_P + std::max((size_t)max_parts * QB * ldw, narrow_parts) * sizeof(R);
     {   // capacity check before anything is modified
         const size_t limit = ctx().smem_optin > 20480 ? ctx().smem_optin - 20480 : 0;
         const int64_t cap = (int64_t)(limit / (QLD * sizeof(R)));
@@ -434,7 +444,6 @@ int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaS
     R* dN = reinterpret_cast<R*>((char*)ws + off_N);
     R* dW = reinterpret_cast<R*>((char*)ws + off_W);
     R* dP = reinterpret_cast<R*>((char*)ws + off_P);
-    const long long part_stride = (long long)QB * ldw;
     // One block of lookahead, as in the LU sweep (blocked.cu): the panel of block b+1 (stream P, high priority, one
     // cluster = 16 SMs) runs under the bulk of block b's trailing update (stream M).
     //   M: wait panel(b) | pack | update(next block's columns) -> EN | update(rest)
@@ -454,14 +463,19 @@ int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaS
     // C (rows x ncols at c) := (I - V T^T V^T) C with the packed reflectors of the current block
     auto update = [&](int64_t rows, R* c, int64_t ncols, const R* T) -> int {
         if (ncols <= 0) return LAIR_B200_OK;
-        const int nparts = (int)((rows + VT_RC - 1) / VT_RC);
+        // a narrow update (the lookahead's next block) sits on the panel -> update -> panel chain: smaller row chunks
+        // put more CTAs on it (its partial buffer is 32 columns wide, so more chunks still fit)
+        const bool narrow = ncols <= QB;
+        const int rc = narrow ? 128 : VT_RC;
+        const int nparts = (int)((rows + rc - 1) / rc);
+        const long long ldp = narrow ? QB : ldw, pstride = (long long)QB * ldp;
         {   // W = V^T C as partial products over row chunks, summed inside the T^T kernel
             ProfScope prof(kProfTrsm, M, 2.0 * QB * (double)ncols * (double)rows);
             dim3 grid((unsigned)((ncols + VT_BN - 1) / VT_BN), (unsigned)nparts);
-            qr_vtc_kernel<R><<<grid, VT_THREADS, 0, M>>>(dV, c, (long long)lda, (int)rows, (int)ncols, dP, (long long)ldw, part_stride);
+            qr_vtc_kernel<R><<<grid, VT_THREADS, 0, M>>>(dV, c, (long long)lda, (int)rows, (int)ncols, dP, ldp, pstride, rc);
             LAIR_LAUNCH_CHECK();
         }
-        qr_trmm_tt_kernel<R><<<(unsigned)((ncols + 127) / 128), 128, 0, M>>>(T, dP, part_stride, nparts, dW, (long long)ldw, (int)ncols);  // W := T^T W
+        qr_trmm_tt_kernel<R><<<(unsigned)((ncols + QB - 1) / QB), 128, 0, M>>>(T, dP, pstride, ldp, nparts, dW, (long long)ldw, (int)ncols);  // W := T^T W
         LAIR_LAUNCH_CHECK();
         return gemm_minus_dev<R>(rows, ncols, QB, dV, QB, dW, ldw, c, lda, M);              // C -= V W
     };
@@ -554,7 +568,7 @@ int qr_q_blocked_dev(int64_t m, int64_t n, const R* d_qr, int64_t ldqr, const R*
                                                                                                             (long long)QB * ldw);
             LAIR_LAUNCH_CHECK();
         }
-        qr_trmm_tt_kernel<R, false><<<(unsigned)((nc + 127) / 128), 128, 0, s>>>(dT, dP, (long long)QB * ldw, nparts, dW, (long long)ldw, (int)nc);
+        qr_trmm_tt_kernel<R, false><<<(unsigned)((nc + QB - 1) / QB), 128, 0, s>>>(dT, dP, (long long)QB * ldw, (long long)ldw, nparts, dW, (long long)ldw, (int)nc);
         LAIR_LAUNCH_CHECK();
         LAIR_CHECK(gemm_minus_dev<R>(rows, nc, QB, dV, QB, dW, ldw, qs, ldq, s));
     }
