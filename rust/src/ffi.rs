@@ -33,6 +33,16 @@ extern "C" {
     pub fn lair_b200_lu_factors(handle: *mut c_void, lu: *mut c_void, rs: i64, cs: i64) -> c_int;
     pub fn lair_b200_lu_view(handle: *mut c_void, view: c_int, out: *mut c_void, rs: i64, cs: i64) -> c_int;
     pub fn lair_b200_lu_destroy(handle: *mut c_void) -> c_int;
+
+    // Householder QR (include/lair_b200.h, "Householder QR"): geqrf in place + tau, q from the factors
+    pub fn lair_b200_sgeqrf(m: i64, n: i64, a: *mut f32, rs: i64, cs: i64, tau: *mut f32) -> c_int;
+    pub fn lair_b200_dgeqrf(m: i64, n: i64, a: *mut f64, rs: i64, cs: i64, tau: *mut f64) -> c_int;
+    pub fn lair_b200_cgeqrf(m: i64, n: i64, a: *mut c_void, rs: i64, cs: i64, tau: *mut c_void) -> c_int;
+    pub fn lair_b200_zgeqrf(m: i64, n: i64, a: *mut c_void, rs: i64, cs: i64, tau: *mut c_void) -> c_int;
+    pub fn lair_b200_sqr_q(m: i64, n: i64, qr: *const f32, rs: i64, cs: i64, tau: *const f32, q: *mut f32, q_rs: i64, q_cs: i64) -> c_int;
+    pub fn lair_b200_dqr_q(m: i64, n: i64, qr: *const f64, rs: i64, cs: i64, tau: *const f64, q: *mut f64, q_rs: i64, q_cs: i64) -> c_int;
+    pub fn lair_b200_cqr_q(m: i64, n: i64, qr: *const c_void, rs: i64, cs: i64, tau: *const c_void, q: *mut c_void, q_rs: i64, q_cs: i64) -> c_int;
+    pub fn lair_b200_zqr_q(m: i64, n: i64, qr: *const c_void, rs: i64, cs: i64, tau: *const c_void, q: *mut c_void, q_rs: i64, q_cs: i64) -> c_int;
 }
 
 /// The reference signatures have no error channel for runtime failure, so a non-zero status

@@ -1,8 +1,10 @@
-//! Crate-private LAPACK-named drivers of the LU path (reference: src/lapack.rs:40-47).
+//! Crate-private LAPACK-named drivers of the LU path and of geqrf (reference: src/lapack.rs:40-47).
+mod geqrf;
 mod getrf;
 mod getrs;
 mod laswp;
 
+pub use geqrf::{geqrf, qr_q};
 pub use getrf::getrf;
 pub use getrs::getrs;
 pub use laswp::laswp;
