@@ -266,6 +266,7 @@ int check_fault(cudaStream_t s);
 // Householder QR (qr.cu): geqrf.rs:9-30 in place on a row-major device matrix, tau on the device;
 // qr::Factorized::q (qr.rs:27-59) into a dense m x m device matrix
 template <class T> int geqrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, T* d_tau, cudaStream_t s);
+template <class T> int geqrf_unblocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, T* d_tau, cudaStream_t s);  // one reflector at a time
 template <class R> int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaStream_t s);  // f32 / f64 (qr_blocked.cu)
 template <class R> int qr_q_blocked_dev(int64_t m, int64_t n, const R* d_qr, int64_t ldqr, const R* d_tau, R* d_q, int64_t ldq, cudaStream_t s);
 template <class T> int qr_q_dev(int64_t m, int64_t n, const T* d_qr, int64_t ldqr, const T* d_tau, T* d_q, int64_t ldq, cudaStream_t s);

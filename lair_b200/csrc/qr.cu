@@ -185,10 +185,94 @@ __global__ void q_column_kernel(T* __restrict__ Q, long long ldq, int m, int i, 
     }
 }
 
+// The same reflector application split over row chunks for tall blocks with few columns (a 65 536 x 256 matrix gives
+// the column-parallel kernel 4 CTAs): pass 1 writes the partial dot products of every (column tile, row chunk), pass 2
+// sums them in chunk order and updates its chunk.
+constexpr int QR_RCHUNK = 1024;
+template <class T>
+__global__ void __launch_bounds__(QR_THREADS)
+larf_dot_kernel(const T* __restrict__ V, long long ldv, const T* __restrict__ tau, const T* __restrict__ C, long long ldc, int rows, int ncols,
+                T* __restrict__ part /* [chunks][ncols] */) {
+    using O = Ops<T>;
+    __shared__ T red[QR_ROWG][QR_COLS];
+    if (O::is_zero(*tau)) return;
+    const int tx = threadIdx.x % QR_COLS, ty = threadIdx.x / QR_COLS;
+    const int col = blockIdx.x * QR_COLS + tx;
+    const int r0 = blockIdx.y * QR_RCHUNK, r1 = min(rows, r0 + QR_RCHUNK);
+    T acc = O::zero();
+    if (col < ncols) {
+        for (int r = r0 + ty; r < r1; r += QR_ROWG) {
+            const T v = r == 0 ? O::one() : V[(long long)r * ldv];
+            acc = O::add(acc, O::mul(conj_s(C[(long long)r * ldc + col]), v));
+        }
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < ncols) {
+        T w = red[0][tx];
+#pragma unroll
+        for (int g = 1; g < QR_ROWG; ++g) w = O::add(w, red[g][tx]);
+        part[(long long)blockIdx.y * ncols + col] = w;
+    }
+}
+template <class T>
+__global__ void __launch_bounds__(QR_THREADS)
+larf_apply_kernel(const T* __restrict__ V, long long ldv, const T* __restrict__ tau, int conj_tau, T* __restrict__ C, long long ldc, int rows,
+                  int ncols, const T* __restrict__ part, int nchunks) {
+    using O = Ops<T>;
+    T t = *tau;
+    if (O::is_zero(t)) return;
+    if (conj_tau) t = conj_s(t);
+    const int tx = threadIdx.x % QR_COLS, ty = threadIdx.x / QR_COLS;
+    const int col = blockIdx.x * QR_COLS + tx;
+    if (col >= ncols) return;
+    T w = O::zero();
+    for (int c = 0; c < nchunks; ++c) w = O::add(w, part[(long long)c * ncols + col]);
+    const T wc = conj_s(w);
+    const T nt = neg_s(t);
+    const int r0 = blockIdx.y * QR_RCHUNK, r1 = min(rows, r0 + QR_RCHUNK);
+    for (int r = r0 + ty; r < r1; r += QR_ROWG) {
+        const T v = r == 0 ? O::one() : V[(long long)r * ldv];
+        T* c = &C[(long long)r * ldc + col];
+        *c = O::add(*c, O::mul(O::mul(nt, v), wc));
+    }
+}
+
+// partial-product scratch of the row-split path: one grow-only buffer per stream role (caller's stream / lookahead stream)
+template <class T>
+int larf_scratch(size_t elems, T** out, cudaStream_t s) {
+    struct Buf { void* p = nullptr; size_t bytes = 0; };
+    static Buf bufs[2];
+    Buf& b = bufs[s == ctx().aux_stream ? 1 : 0];
+    const size_t bytes = elems * sizeof(T);
+    if (b.bytes < bytes) {
+        if (b.p) {
+            LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+            LAIR_CUDA_CHECK(cudaFree(b.p));
+            b = Buf{};
+        }
+        LAIR_CUDA_CHECK(cudaMalloc(&b.p, bytes * 2 + 256));
+        b.bytes = bytes * 2 + 256;
+    }
+    *out = static_cast<T*>(b.p);
+    return LAIR_B200_OK;
+}
+
 template <class T>
 int larf_left_dev(const T* d_v, int64_t ldv, const T* d_tau, bool conj_tau, T* d_c, int64_t ldc, int64_t rows, int64_t ncols, cudaStream_t s) {
     if (rows <= 0 || ncols <= 0) return LAIR_B200_OK;
     const unsigned grid = (unsigned)((ncols + QR_COLS - 1) / QR_COLS);
+    if (rows >= 4 * QR_RCHUNK && (int)grid * 2 <= ctx().sm_count) {  // tall and narrow: split the rows as well
+        const int nchunks = (int)((rows + QR_RCHUNK - 1) / QR_RCHUNK);
+        T* part = nullptr;
+        LAIR_CHECK(larf_scratch<T>((size_t)nchunks * (size_t)ncols, &part, s));
+        larf_dot_kernel<T><<<dim3(grid, (unsigned)nchunks), QR_THREADS, 0, s>>>(d_v, (long long)ldv, d_tau, d_c, (long long)ldc, (int)rows, (int)ncols, part);
+        LAIR_LAUNCH_CHECK();
+        larf_apply_kernel<T><<<dim3(grid, (unsigned)nchunks), QR_THREADS, 0, s>>>(d_v, (long long)ldv, d_tau, conj_tau ? 1 : 0, d_c, (long long)ldc, (int)rows,
+                                                                              (int)ncols, part, nchunks);
+        LAIR_LAUNCH_CHECK();
+        return LAIR_B200_OK;
+    }
     larf_left_kernel<T><<<grid, QR_THREADS, 0, s>>>(d_v, (long long)ldv, d_tau, conj_tau ? 1 : 0, d_c, (long long)ldc, (int)rows, (int)ncols);
     LAIR_LAUNCH_CHECK();
     return LAIR_B200_OK;
@@ -209,6 +293,13 @@ int geqrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, T* d_tau, cudaStream_t 
             if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
         }
     }
+    return geqrf_unblocked_dev<T>(m, n, d_a, lda, d_tau, s);
+}
+
+// the reference's loop, one reflector at a time (also the panel of the blocked sweep when it does not fit one cluster)
+template <class T>
+int geqrf_unblocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, T* d_tau, cudaStream_t s) {
+    const int64_t k = m < n ? m : n;
     ProfScope prof(kProfSmall, s, 2.0 * (double)m * (double)n * (double)k);
     for (int64_t i = 0; i < k; ++i) {
         T* aii = d_a + i * lda + i;
@@ -242,6 +333,7 @@ int qr_q_dev(int64_t m, int64_t n, const T* d_qr, int64_t ldqr, const T* d_tau, 
 
 #define INST(T)                                                                        \
     template int geqrf_dev<T>(int64_t, int64_t, T*, int64_t, T*, cudaStream_t);         \
+    template int geqrf_unblocked_dev<T>(int64_t, int64_t, T*, int64_t, T*, cudaStream_t); \
     template int qr_q_dev<T>(int64_t, int64_t, const T*, int64_t, const T*, T*, int64_t, cudaStream_t);
 INST(float)
 INST(double)

@@ -213,7 +213,7 @@ __global__ void qr_pack_kernel(const R* __restrict__ A, long long lda, int rows,
         R v = R(0);
         if (k < w) v = r < k ? R(0) : (r == k ? R(1) : A[(long long)r * lda + k]);
         Vp[idx] = v;
-        NVt[(long long)k * ldt + r] = -v;
+        if (NVt) NVt[(long long)k * ldt + r] = -v;
     }
 }
 
@@ -420,28 +420,23 @@ int qr_panel_dev(int64_t rows, int64_t w, R* d_a, int64_t lda, R* d_tau, R* d_T,
 
 }  // namespace
 
-// Returns LAIR_B200_ERR_UNSUPPORTED (nothing done, no error set) when the first panel does not fit one cluster.
 template <class R>
 int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaStream_t s) {
     const int64_t k = m < n ? m : n;
     if (k == 0) return LAIR_B200_OK;
-    // workspace: T (2 x QB x QB) | Vp (m x QB) | NVt (QB x ldt, unused by the default path) | W (QB x n) | Wp (nparts x QB x n)
+    // workspace: T (2 x QB x QB) | Vp (m x QB) | (spare, QB x ldt) | W (QB x n) | Wp (nparts x QB x n) | V2, Gram partials (fallback panel)
     const int64_t ldt = (m + 3) / 4 * 4, ldw = (n + 3) / 4 * 4;
     const int64_t max_parts = (m + VT_RC - 1) / VT_RC;
     const size_t off_T = 0, off_V = 4096 * sizeof(R), off_N = off_V + (size_t)m * QB * sizeof(R), off_W = off_N + (size_t)QB * ldt * sizeof(R);
     const size_t off_P = off_W + (size_t)QB * ldw * sizeof(R);
     const size_t narrow_parts = (size_t)((m + 127) / 128) * QB * QB;  // the lookahead's narrow updates: 128-row chunks, 32 columns
-    const size_t total = off_P + std::max((size_t)max_parts * QB * ldw, narrow_parts) * sizeof(R);
-    {   // capacity check before anything is modified
-        const size_t limit = ctx().smem_optin > 20480 ? ctx().smem_optin - 20480 : 0;
-        const int64_t cap = (int64_t)(limit / (QLD * sizeof(R)));
-        if ((m + QMAXC - 1) / QMAXC > cap) return LAIR_B200_ERR_UNSUPPORTED;
-    }
+    const size_t off_V2 = off_P + std::max((size_t)max_parts * QB * ldw, narrow_parts) * sizeof(R);  // fallback panel: its own V ...
+    const size_t off_P2 = off_V2 + (size_t)m * QB * sizeof(R);                                        // ... and Gram partials
+    const size_t total = off_P2 + (size_t)max_parts * QB * QB * sizeof(R);
     void* ws = nullptr;
     LAIR_CHECK(qr_workspace(total, &ws, s));
     R* dT[2] = {reinterpret_cast<R*>((char*)ws + off_T), reinterpret_cast<R*>((char*)ws + off_T) + 2048};
     R* dV = reinterpret_cast<R*>((char*)ws + off_V);
-    R* dN = reinterpret_cast<R*>((char*)ws + off_N);
     R* dW = reinterpret_cast<R*>((char*)ws + off_W);
     R* dP = reinterpret_cast<R*>((char*)ws + off_P);
     // One block of lookahead, as in the LU sweep (blocked.cu): the panel of block b+1 (stream P, high priority, one
@@ -452,13 +447,25 @@ int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaS
     const bool look = ctx().opt.lookahead != 0 && k > QB;
     cudaStream_t M = s, P = look ? ctx().aux_stream : s;
     cudaEvent_t EP = ctx().ev[0], EN = ctx().ev[1];
+    R* dV2 = reinterpret_cast<R*>((char*)ws + off_V2);
+    R* dP2 = reinterpret_cast<R*>((char*)ws + off_P2);
     auto panel = [&](int64_t j0, int64_t jb, int buf, cudaStream_t st) -> int {
-        const int rc = qr_panel_dev<R>(m - j0, jb, d_a + j0 * lda + j0, lda, d_tau + j0, dT[buf], st);
-        if (rc == LAIR_B200_ERR_UNSUPPORTED) {
-            set_error("geqrf: panel of %lld rows does not fit one cluster", (long long)(m - j0));
-            return LAIR_B200_ERR_CUDA;
-        }
-        return rc;
+        const int64_t rows = m - j0;
+        R* ajj = d_a + j0 * lda + j0;
+        const int rc = qr_panel_dev<R>(rows, jb, ajj, lda, d_tau + j0, dT[buf], st);
+        if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
+        // A panel too tall for the shared memory of one cluster: the one-reflector loop on the panel's columns (its
+        // reflector application splits the rows over CTAs, qr.cu), then T from tau and V^T V as in qr_q_blocked_dev.
+        LAIR_CHECK(geqrf_unblocked_dev<R>(rows, jb, ajj, lda, d_tau + j0, st));
+        const unsigned pb = (unsigned)std::min<int64_t>((rows * QB + 255) / 256, (int64_t)ctx().sm_count * 8);
+        qr_pack_kernel<R><<<pb, 256, 0, st>>>(ajj, (long long)lda, (int)rows, (int)jb, dV2, (R*)nullptr, 0);
+        LAIR_LAUNCH_CHECK();
+        const int nparts = (int)((rows + VT_RC - 1) / VT_RC);
+        qr_vtc_kernel<R><<<dim3(1, (unsigned)nparts), VT_THREADS, 0, st>>>(dV2, dV2, (long long)QB, (int)rows, QB, dP2, (long long)QB, (long long)QB * QB);
+        LAIR_LAUNCH_CHECK();
+        qr_build_t_kernel<R><<<1, QB * QB, 0, st>>>(dP2, (long long)QB * QB, nparts, d_tau + j0, (int)jb, dT[buf]);
+        LAIR_LAUNCH_CHECK();
+        return LAIR_B200_OK;
     };
     // C (rows x ncols at c) := (I - V T^T V^T) C with the packed reflectors of the current block
     auto update = [&](int64_t rows, R* c, int64_t ncols, const R* T) -> int {
@@ -497,7 +504,7 @@ int geqrf_blocked_dev(int64_t m, int64_t n, R* d_a, int64_t lda, R* d_tau, cudaS
         }
         if (c0 >= n) break;
         const unsigned pb = (unsigned)std::min<int64_t>((rows * QB + 255) / 256, (int64_t)ctx().sm_count * 8);
-        qr_pack_kernel<R><<<pb, 256, 0, M>>>(ajj, (long long)lda, (int)rows, (int)jb, dV, dN, (long long)ldt);
+        qr_pack_kernel<R><<<pb, 256, 0, M>>>(ajj, (long long)lda, (int)rows, (int)jb, dV, (R*)nullptr, 0);
         LAIR_LAUNCH_CHECK();
         if (nb2 > 0) {
             LAIR_CHECK(update(rows, ajj + jb, nb2, dT[buf]));        // the next block's columns first ...
@@ -542,7 +549,6 @@ int qr_q_blocked_dev(int64_t m, int64_t n, const R* d_qr, int64_t ldqr, const R*
     R* dV = reinterpret_cast<R*>((char*)ws + off_V);
     R* dW = reinterpret_cast<R*>((char*)ws + off_W);
     R* dP = reinterpret_cast<R*>((char*)ws + off_P);
-    R* dN = dP;  // qr_pack_kernel also writes -V^T; it is not needed here and lands in the partial buffer before it is used
     const unsigned ib = (unsigned)std::min<int64_t>((m * m + 255) / 256, (int64_t)ctx().sm_count * 8);
     q_identity_kernel<R><<<ib, 256, 0, s>>>(d_q, (long long)ldq, (int)m);
     LAIR_LAUNCH_CHECK();
@@ -553,7 +559,7 @@ int qr_q_blocked_dev(int64_t m, int64_t n, const R* d_qr, int64_t ldqr, const R*
         const int64_t rows = m - j0, nc = m - j0;
         const int nparts = (int)((rows + VT_RC - 1) / VT_RC);
         const unsigned pb = (unsigned)std::min<int64_t>((rows * QB + 255) / 256, (int64_t)ctx().sm_count * 8);
-        qr_pack_kernel<R><<<pb, 256, 0, s>>>(d_qr + j0 * ldqr + j0, (long long)ldqr, (int)rows, (int)jb, dV, dN, (long long)rows);
+        qr_pack_kernel<R><<<pb, 256, 0, s>>>(d_qr + j0 * ldqr + j0, (long long)ldqr, (int)rows, (int)jb, dV, (R*)nullptr, 0);
         LAIR_LAUNCH_CHECK();
         // T from tau and V^T V
         qr_vtc_kernel<R><<<dim3(1, (unsigned)nparts), VT_THREADS, 0, s>>>(dV, dV, (long long)QB, (int)rows, QB, dP, (long long)QB, (long long)QB * QB);

@@ -132,3 +132,26 @@ def test_geqrf_blocked_equals_unblocked(lair, dt, shape):
         fact, orth = qr_errors(a0, q, np.triu(out[1][0]))
         fact_o, orth_o = qr_errors(a0, oracle.qr_q(ref, tau_o), np.triu(ref))
         assert fact <= 10 * max(fact_o, 0.01) and orth <= 10 * max(orth_o, 0.01), (fact, fact_o, orth, orth_o)
+
+
+@pytest.mark.parametrize("dt,shape", [(np.float64, (14000, 96)), (np.float32, (30000, 64)), (np.complex128, (9000, 40))])
+def test_geqrf_tall_panels(lair, dt, shape):
+    """Panels taller than one cluster's shared memory (f64 > ~12 800 rows, f32 > ~25 600): the blocked sweep factors the
+    panel with the one-reflector loop, whose reflector application splits the rows over CTAs (two passes with in-order
+    partial sums), and rebuilds T from tau and V^T V.  R, the reflectors and tau against the oracle; A = QR checked
+    through R^H R = A^H A (Q would be m x m)."""
+    rng = np.random.default_rng(shape[0])
+    a0 = _rand(rng, shape, dt, "normal")
+    qr = a0.copy()
+    tau = lair.lapack.geqrf(qr)
+    ref = a0.copy()
+    tau_o = oracle.geqrf(ref)
+    eps = np.finfo(dt).eps
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(qr - ref)) <= 100 * eps * np.sqrt(shape[0]) * shape[1] * scale
+    assert np.max(np.abs(tau - tau_o)) <= 100 * eps * np.sqrt(shape[0]) * shape[1]
+    wide = np.complex128 if np.iscomplexobj(a0) else np.float64
+    r = np.triu(qr[: shape[1]]).astype(wide)
+    a = a0.astype(wide)
+    gram = np.linalg.norm(r.conj().T @ r - a.conj().T @ a) / (np.linalg.norm(a) ** 2)
+    assert gram <= 100 * eps, gram
