@@ -59,30 +59,12 @@ __global__ void pack_b_kernel(const cx<R>* __restrict__ B, long long ldb, int k,
     }
 }
 
-struct PackBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-};
-// grow-only device buffers of the packed operands (one pair per stream role; every use is ordered on its stream)
+// grow-only device buffers of the packed operands, owned by the context (one pair per stream role: the caller's stream
+// and the lookahead stream run concurrently; every use is ordered on its stream)
 int pack_buffers(size_t a_bytes, size_t b_bytes, void** pa, void** pb, cudaStream_t s) {
-    static PackBuf all[2][2];  // [0]: the caller's stream, [1]: the lookahead stream -- the two run concurrently
-    PackBuf* bufs = all[s == ctx().aux_stream ? 1 : 0];
-    const size_t want[2] = {a_bytes, b_bytes};
-    for (int i = 0; i < 2; ++i) {
-        if (bufs[i].bytes < want[i]) {
-            if (bufs[i].p) {
-                LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
-                LAIR_CUDA_CHECK(cudaFree(bufs[i].p));
-                bufs[i] = PackBuf{};
-            }
-            const size_t sz = want[i] + want[i] / 4 + 256;
-            LAIR_CUDA_CHECK(cudaMalloc(&bufs[i].p, sz));
-            bufs[i].bytes = sz;
-        }
-    }
-    *pa = bufs[0].p;
-    *pb = bufs[1].p;
-    return LAIR_B200_OK;
+    const bool aux = s == ctx().aux_stream;
+    LAIR_CHECK(ensure_work(aux ? Context::kWorkCxPackA1 : Context::kWorkCxPackA0, a_bytes, pa, s));
+    return ensure_work(aux ? Context::kWorkCxPackB1 : Context::kWorkCxPackB0, b_bytes, pb, s);
 }
 
 // C (m x n) -= A (m x k) * B (k x n), complex, row-major

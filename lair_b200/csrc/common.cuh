@@ -178,12 +178,18 @@ struct Context {
     // generic device scratch grown on demand
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // grow-only work buffers with fixed roles (ensure_work): owned by the context so shutdown releases them
+    enum WorkSlot { kWorkCxPackA0 = 0, kWorkCxPackB0, kWorkCxPackA1, kWorkCxPackB1, kWorkQr, kWorkLarf0, kWorkLarf1, kWorkSlots };
+    void* work[kWorkSlots] = {};
+    size_t work_bytes[kWorkSlots] = {};
     Options opt;
 };
 
 Context& ctx();
 int ensure_init();                                  // binds to the current device if needed
 int ensure_scratch(size_t bytes, void** out);       // device scratch >= bytes (may reallocate)
+// work buffer `slot` >= bytes; a buffer that has to grow is released after `s` has drained (its users are ordered on s)
+int ensure_work(int slot, size_t bytes, void** out, cudaStream_t s);
 
 // ---- kernels / device-resident routines (row-major, leading dimension in elements) --------
 template <class T> int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);

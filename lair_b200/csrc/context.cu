@@ -124,6 +124,24 @@ int ensure_scratch(size_t bytes, void** out) {
     return LAIR_B200_OK;
 }
 
+int ensure_work(int slot, size_t bytes, void** out, cudaStream_t s) {
+    Context& c = g_ctx;
+    LAIR_REQUIRE(slot >= 0 && slot < Context::kWorkSlots, "ensure_work: bad slot %d", slot);
+    if (c.work_bytes[slot] < bytes) {
+        if (c.work[slot]) {
+            LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
+            LAIR_CUDA_CHECK(cudaFree(c.work[slot]));
+            c.work[slot] = nullptr;
+            c.work_bytes[slot] = 0;
+        }
+        const size_t want = bytes + (bytes >> 2) + 256;
+        LAIR_CUDA_CHECK(cudaMalloc(&c.work[slot], want));
+        c.work_bytes[slot] = want;
+    }
+    *out = c.work[slot];
+    return LAIR_B200_OK;
+}
+
 }  // namespace lair
 
 using namespace lair;
@@ -162,6 +180,8 @@ int lair_b200_shutdown(void) {
     cudaDeviceSynchronize();
     if (c.panel_ws) cudaFree(c.panel_ws);
     if (c.scratch) cudaFree(c.scratch);
+    for (auto& w : c.work)
+        if (w) cudaFree(w);
     for (auto& ev : c.ev)
         if (ev) cudaEventDestroy(ev);
     if (c.stream) cudaStreamDestroy(c.stream);

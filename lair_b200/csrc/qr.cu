@@ -238,23 +238,12 @@ larf_apply_kernel(const T* __restrict__ V, long long ldv, const T* __restrict__ 
     }
 }
 
-// partial-product scratch of the row-split path: one grow-only buffer per stream role (caller's stream / lookahead stream)
+// partial-product scratch of the row-split path: one context-owned buffer per stream role (caller's stream / lookahead stream)
 template <class T>
 int larf_scratch(size_t elems, T** out, cudaStream_t s) {
-    struct Buf { void* p = nullptr; size_t bytes = 0; };
-    static Buf bufs[2];
-    Buf& b = bufs[s == ctx().aux_stream ? 1 : 0];
-    const size_t bytes = elems * sizeof(T);
-    if (b.bytes < bytes) {
-        if (b.p) {
-            LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
-            LAIR_CUDA_CHECK(cudaFree(b.p));
-            b = Buf{};
-        }
-        LAIR_CUDA_CHECK(cudaMalloc(&b.p, bytes * 2 + 256));
-        b.bytes = bytes * 2 + 256;
-    }
-    *out = static_cast<T*>(b.p);
+    void* p = nullptr;
+    LAIR_CHECK(ensure_work(s == ctx().aux_stream ? Context::kWorkLarf1 : Context::kWorkLarf0, elems * sizeof(T), &p, s));
+    *out = static_cast<T*>(p);
     return LAIR_B200_OK;
 }
 

@@ -350,24 +350,7 @@ qr_build_t_kernel(const R* __restrict__ Gp, long long part_stride, int nparts, c
     T[i * QB + k] = Ts[i][k];
 }
 
-struct QrWork {
-    void* p = nullptr;
-    size_t bytes = 0;
-};
-int qr_workspace(size_t bytes, void** out, cudaStream_t s) {
-    static QrWork wk;
-    if (wk.bytes < bytes) {
-        if (wk.p) {
-            LAIR_CUDA_CHECK(cudaStreamSynchronize(s));
-            LAIR_CUDA_CHECK(cudaFree(wk.p));
-            wk = QrWork{};
-        }
-        LAIR_CUDA_CHECK(cudaMalloc(&wk.p, bytes + bytes / 4 + 256));
-        wk.bytes = bytes + bytes / 4 + 256;
-    }
-    *out = wk.p;
-    return LAIR_B200_OK;
-}
+int qr_workspace(size_t bytes, void** out, cudaStream_t s) { return ensure_work(Context::kWorkQr, bytes, out, s); }
 
 template <class R>
 int qr_panel_dev(int64_t rows, int64_t w, R* d_a, int64_t lda, R* d_tau, R* d_T, cudaStream_t s) {
