@@ -149,7 +149,13 @@ def _barrier(world: int):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_c2(n_sample: int = 2048, nrhs: int = NRHS_C2, seed: int = 1):
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the batched kernel over 10^6 matrices,
+# from the committed `ncu --set full` capture (profiles/r1c_ncu_full_metrics.txt): f32 4.263 + 4.170 GB
+# against 8.32 GB algorithmic, f64 9.053 + 8.268 GB against 16.51 GB.
+NCU_TRAFFIC_C3 = {"f32": 4262975000 + 4169763000, "f64": 9052583000 + 8267601000}
+
+
+def cpu_sample_c2(n_sample: int = 4096, nrhs: int = NRHS_C2, seed: int = 1):
     """The oracle on a bounded sample of the c2 workload: n_sample x n_sample f64 getrf + nrhs
     single-RHS getrs calls (the reference has no multi-RHS getrs), ONE core."""
     import oracle
@@ -168,11 +174,13 @@ def run_reference(args, rank: int, world: int):
         return
     for _ in range(min(args.warmup, 1)):
         cpu_sample_c2(512)
+    # each step is a bounded sample; with many steps the sample shrinks so the run ends within minutes
+    ref_n = args.ref_n if args.steps <= 8 else min(args.ref_n, 3072) if args.steps <= 24 else min(args.ref_n, 2048)
     vals = []
     t0 = time.perf_counter()
     sample = ""
     for _ in range(args.steps):
-        g, tg, ts, sample = cpu_sample_c2(args.ref_n)
+        g, tg, ts, sample = cpu_sample_c2(ref_n)
         vals.append((g, tg + ts))
     wall = time.perf_counter() - t0
     gflops = float(np.mean([v[0] for v in vals]))
@@ -181,7 +189,7 @@ def run_reference(args, rank: int, world: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10)",
         "config": {"workload": (f"c2 getrf+getrs f64 n={N_C2} nrhs={NRHS_C2}" if world == 1 else f"c4 getrf f64 n={args.n}") +
-                               f" (bounded sample: n={args.ref_n} getrf + {NRHS_C2} getrs; the reference is O(n^3) scalar code, "
+                               f" (bounded sample: n={ref_n} getrf + {NRHS_C2} getrs; the reference is O(n^3) scalar code, "
                                "n=8192 would take minutes and n=65536 ~35 h on one core)", "inputs": "host"},
         "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -403,11 +411,12 @@ def run_c3(args, rank: int, world: int, local: int):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle
-        smp = a0[:20000].cpu().numpy()
+        smp = a0[:min(batch, args.ref_batch)].cpu().numpy()
         t0 = time.perf_counter()
         oracle.getrf_batched(smp)
         t = time.perf_counter() - t0
-        cpu = {"value": len(smp) / t, "unit": "mats/s", "cores": 1, "kind": "port", "sample": "20000 matrices, 1 thread"}
+        cpu = {"value": len(smp) / t, "unit": "mats/s", "cores": 1, "kind": "port",
+               "sample": f"{len(smp)} matrices of the same batch ({t:.1f} s), 1 thread"}
     if rank == 0:
         line = {
             "metric": "batched_lu32_mats_per_s", "value": value, "unit": "mats/s", "n_gpus": world, "steps": args.steps,
@@ -416,7 +425,11 @@ def run_c3(args, rank: int, world: int, local: int):
             "config": {"workload": f"c3: batched getrf {args.dtype} 10^6 x 32x32, batch sharded over ranks",
                        "l2": "per-rank input exceeds L2 at N<=4; restore copy outside the timed region"},
             "roofline": {"bound": "hbm", "kernel": "batched_lu32_v6_f32 / _f64 (batched_lu4.cu)", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None},
+                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_C3[args.dtype] if batch == 1_000_000 else None,
+                         "traffic_unit": "bytes per launch of 10^6 matrices (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": "profiles/r1c_ncu_full_metrics.txt (ncu --set full capture of this kernel at this size)",
+                         "algorithmic_bytes_per_launch": int(batch * bpm)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -582,7 +595,8 @@ def main():
     ap.add_argument("--order", dest="n", type=int, default=65536, help="matrix order n of the c4 workload")
     ap.add_argument("--block", dest="nb", type=int, default=256, help="block-cyclic block width of the c4 workload")
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
-    ap.add_argument("--ref-n", type=int, default=2048, help="sample size of the CPU (oracle) leg")
+    ap.add_argument("--ref-batch", type=int, default=1_000_000, help="matrices in the CPU (oracle) leg of the c3 workload")
+    ap.add_argument("--ref-n", type=int, default=4096, help="sample size of the CPU (oracle) leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ncu-step", action="store_true",
