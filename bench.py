@@ -153,6 +153,9 @@ def _barrier(world: int):
 # from the committed `ncu --set full` capture (profiles/r1c_ncu_full_metrics.txt): f32 4.263 + 4.170 GB
 # against 8.32 GB algorithmic, f64 9.053 + 8.268 GB against 16.51 GB.
 NCU_TRAFFIC_C3 = {"f32": 4262975000 + 4169763000, "f64": 9052583000 + 8267601000}
+# same counters for the largest DMMA GEMM launch of the c2 step (7808 x 7680 x 128; profiles/r1_final_ncu_full_metrics.txt):
+# 498.7 MB read + 427.7 MB written against 959 MB of algorithmic C read + write (A and B panels stay in L2).
+NCU_TRAFFIC_C2_GEMM = 498718976 + 427666176
 
 
 def cpu_sample_c2(n_sample: int = 4096, nrhs: int = NRHS_C2, seed: int = 1):
@@ -332,7 +335,11 @@ def run_c2(args, rank: int, world: int, local: int):
                          "frac": gemm_tflops / FP64_PEAK_TFLOPS,
                          "peak_source": "FP64 DMMA issue-rate microbench on this pool's B200 (profiles/r1_microbench_fp64_peak.jsonl); "
                                         "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM reaches 35.5",
-                         "launches": gemm["launches"], "kernel_ms_in_step": gemm["ms"], "traffic": None,
+                         "launches": gemm["launches"], "kernel_ms_in_step": gemm["ms"],
+                         "traffic": NCU_TRAFFIC_C2_GEMM if n == 8192 else None,
+                         "traffic_unit": "bytes of the step's largest launch (M x N x K = 7808 x 7680 x 128; "
+                                         "dram__bytes_read.sum + dram__bytes_write.sum), algorithmic C read + write = 959 MB",
+                         "traffic_source": "profiles/r1_final_ncu_full_metrics.txt (ncu --set full capture of that launch)",
                          "kernel_ms_by_family": kernel_share},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
