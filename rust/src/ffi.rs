@@ -43,6 +43,30 @@ extern "C" {
     pub fn lair_b200_dqr_q(m: i64, n: i64, qr: *const f64, rs: i64, cs: i64, tau: *const f64, q: *mut f64, q_rs: i64, q_cs: i64) -> c_int;
     pub fn lair_b200_cqr_q(m: i64, n: i64, qr: *const c_void, rs: i64, cs: i64, tau: *const c_void, q: *mut c_void, q_rs: i64, q_cs: i64) -> c_int;
     pub fn lair_b200_zqr_q(m: i64, n: i64, qr: *const c_void, rs: i64, cs: i64, tau: *const c_void, q: *mut c_void, q_rs: i64, q_cs: i64) -> c_int;
+
+    // context queries (include/lair_b200.h, "context")
+    pub fn lair_b200_version() -> c_int;
+    pub fn lair_b200_device_count(count: *mut c_int) -> c_int;
+    pub fn lair_b200_check_fault(stream: *mut c_void) -> c_int;
+
+    // gesv: the whole of equation::solve (src/equation.rs:32-60) in one call; the factors never leave HBM
+    pub fn lair_b200_sgesv(n: i64, nrhs: i64, a: *const f32, a_rs: i64, a_cs: i64, b: *const f32, b_rs: i64, b_cs: i64,
+                           x: *mut f32, x_rs: i64, x_cs: i64, info: *mut i64) -> c_int;
+    pub fn lair_b200_dgesv(n: i64, nrhs: i64, a: *const f64, a_rs: i64, a_cs: i64, b: *const f64, b_rs: i64, b_cs: i64,
+                           x: *mut f64, x_rs: i64, x_cs: i64, info: *mut i64) -> c_int;
+
+    // batched LU of contiguous row-major n x n matrices, n <= 32 (BASELINE configs[2]); int32 pivots / info per matrix
+    pub fn lair_b200_sgetrf_batched(batch: i64, n: i64, a: *mut f32, ipiv: *mut i32, info: *mut i32) -> c_int;
+    pub fn lair_b200_dgetrf_batched(batch: i64, n: i64, a: *mut f64, ipiv: *mut i32, info: *mut i32) -> c_int;
+
+    // one large LU over several GPUs, one process per GPU (BASELINE configs[3]); device pointers
+    pub fn lair_b200_mg_unique_id(id128: *mut c_void) -> c_int;
+    pub fn lair_b200_mg_init(rank: c_int, nranks: c_int, id128: *const c_void) -> c_int;
+    pub fn lair_b200_mg_finalize() -> c_int;
+    pub fn lair_b200_sgetrf_mg_dev(n: i64, nb: i64, d_a_local: *mut f32, lda: i64, d_ipiv: *mut i32, d_info: *mut i32,
+                                   stream: *mut c_void) -> c_int;
+    pub fn lair_b200_dgetrf_mg_dev(n: i64, nb: i64, d_a_local: *mut f64, lda: i64, d_ipiv: *mut i32, d_info: *mut i32,
+                                   stream: *mut c_void) -> c_int;
 }
 
 /// The reference signatures have no error channel for runtime failure, so a non-zero status

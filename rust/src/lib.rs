@@ -5,6 +5,10 @@
 //! `decomposition/lu.rs`, `equation.rs` and `scalar.rs` are the reference's files unchanged
 //! (they only call `lapack::*`), so they are not duplicated in this repository: drop the three
 //! files of `src/lapack/` and `ffi.rs` into the reference tree, add `build.rs`, done.
+//! Optional, same public surface: `equation.rs` (one `gesv` call for f32 / f64 instead of copy +
+//! factor + solve), `decomposition/lu_device.rs` (factors stay in HBM behind a handle) and
+//! `lapack/getrf_batched.rs` (the loop over small matrices as one call) replace / join the
+//! reference's files of the same module paths.
 mod ffi;
 mod lapack;
 
