@@ -86,3 +86,35 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), os.path.join(dirpath, f)
                 assert "lair_oracle" not in text or f.endswith((".cu", ".cuh")) and "oracle/lair_oracle.hpp" in text, os.path.join(dirpath, f)
+
+
+def _split_params(params: str):
+    params = params.strip()
+    return [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+
+
+def test_rust_shim_declarations_match_header():
+    """rust/src/ffi.rs (source-only: no Rust toolchain in the image) binds only symbols the header
+    declares, with the same number of parameters and the same pointer-ness per parameter."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lair_b200.h")).read(), flags=re.S)
+    c_decl = {m.group(1): _split_params(m.group(2))
+              for m in re.finditer(r"LAIR_B200_API\s+[\w\s\*]+?\b(lair_b200_\w+)\s*\(([^)]*)\)", header)}
+    rust = re.sub(r"//.*", "", open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read())
+    block = rust[rust.index('extern "C"'):]
+    r_decl = {m.group(1): _split_params(m.group(2))
+              for m in re.finditer(r"pub fn (lair_b200_\w+)\s*\(([^)]*)\)", block, flags=re.S)}
+    assert len(r_decl) >= 40
+    for name, r_params in r_decl.items():
+        assert name in c_decl, f"{name} is not declared in include/lair_b200.h"
+        c_params = c_decl[name]
+        assert len(r_params) == len(c_params), (name, r_params, c_params)
+        for rp, cp in zip(r_params, c_params):
+            cp = cp.replace("lair_b200_lu_t*", "void**").replace("lair_b200_lu_t", "void*")  # opaque handle typedef
+            assert ("*" in rp) == ("*" in cp), (name, rp, cp)
+            if "*" in cp:
+                assert ("*const" in rp) == cp.startswith("const "), (name, rp, cp)
+    # the drop-in rows of SURVEY 8b are all bound
+    for p in "sdcz":
+        assert f"lair_b200_{p}getrf" in r_decl and f"lair_b200_{p}getrs" in r_decl
+    for p in "sd":
+        assert f"lair_b200_{p}gesv" in r_decl and f"lair_b200_{p}getrf_batched" in r_decl
