@@ -177,7 +177,7 @@ LAIR_B200_API int lair_b200_sgetrf_mg_dev(int64_t n, int64_t nb, float* d_a_loca
 /* Tuning knobs (also read from the environment at init: LAIR_B200_NB, LAIR_B200_SMALL_N).
  * Behaviour: "nb" (outer block width, 0 = by remaining size), "nb_t1"/"nb_t2" (its thresholds),
  * "small_n", "lookahead", "stream_cols"/"stream_join_div" (chunked upload of the host-pointer
- * entry points).  Kernel variants kept for the parity tests and A/B measurements:
+ * entry points), "batched_chunk" (matrices per pipelined chunk of the host-pointer batched LU).  Kernel variants kept for the parity tests and A/B measurements:
  * "batched_cfg", "panel_cluster", "panel_rpt", "panel_group", "panel_exchange", "panel_w64",
  * "panel_timing", "gemm_cfg", "fuse_swap_trsm", "trsm_dataflow", "trsm_rb", "laswp_perm"
  * (meanings next to Options in csrc/common.cuh).  Every variant computes the same result to the

@@ -199,7 +199,7 @@ static int getrf_batched_host(int64_t batch, int64_t n, T* a, int32_t* ipiv, int
     // (copy stream) while chunk i is factored (library stream) and chunk i-1 travels back (third stream).  With pinned
     // host memory the call costs max(H2D, D2H) instead of their sum; pageable memory degrades to the driver's staging.
     constexpr int kHalf = Context::kMaxChunks / 2;  // events [0, kHalf): chunk landed; [kHalf, 2 kHalf): chunk factored
-    int64_t per = 16384;
+    int64_t per = c.opt.batched_chunk;
     if ((batch + per - 1) / per > kHalf) per = (batch + kHalf - 1) / kHalf;
     const int nchunks = (int)((batch + per - 1) / per);
     for (int i = 0; i < 2 * kHalf; ++i)

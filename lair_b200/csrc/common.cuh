@@ -147,6 +147,7 @@ struct Options {
     int64_t panel_exchange = 1; // panel_blocked: 1 = st.async record push + winner-row pull, 0 = cluster barrier + pull
     int64_t stream_cols = 1024; // host-pointer getrf/gesv: upload the matrix in column chunks of this width and start
                                 // factoring when the first has landed (0 = upload everything first)
+    int64_t batched_chunk = 8192; // host-pointer batched LU: matrices per pipelined H2D / factor / D2H chunk (sweep: profiles/r1e_quick_batched_e2e.jsonl)
     int64_t stream_join_div = 4; // a chunk starting at column cs joins the sweep once cs / stream_join_div columns are factored
     int64_t laswp_perm = 1;    // getrs: apply P to the right-hand sides as one collapsed permutation (laswp_perm.cu)
     int64_t fuse_swap_trsm = 1; // block steps of width <= 128: one fused laswp+trsm launch (laswp_trsm.cu)

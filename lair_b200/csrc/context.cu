@@ -243,6 +243,12 @@ int lair_b200_set_option(const char* name, int64_t value) {
             return LAIR_B200_ERR_INVALID;
         }
         o.stream_cols = value;
+    } else if (!strcmp(name, "batched_chunk")) {
+        if (value < 256) {
+            set_error("batched_chunk must be >= 256 matrices, got %lld", (long long)value);
+            return LAIR_B200_ERR_INVALID;
+        }
+        o.batched_chunk = value;
     } else if (!strcmp(name, "stream_join_div")) {
         o.stream_join_div = value < 1 ? 1 : value;
     } else if (!strcmp(name, "laswp_perm")) {
@@ -281,6 +287,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "panel_timing")) *value = o.panel_timing;
     else if (!strcmp(name, "trsm_dataflow")) *value = o.trsm_dataflow;
     else if (!strcmp(name, "stream_cols")) *value = o.stream_cols;
+    else if (!strcmp(name, "batched_chunk")) *value = o.batched_chunk;
     else if (!strcmp(name, "stream_join_div")) *value = o.stream_join_div;
     else if (!strcmp(name, "laswp_perm")) *value = o.laswp_perm;
     else if (!strcmp(name, "trsm_rb")) *value = o.trsm_rb;

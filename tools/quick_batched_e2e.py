@@ -32,12 +32,14 @@ h = rng.uniform(0, 10, size=(nmat, 32, 32))
 w = h.copy()
 assert rt.cudaHostRegister(ctypes.c_void_p(w.ctypes.data), ctypes.c_size_t(w.nbytes), 0) == 0
 lair_b200.lapack.getrf_batched(w)
-ts = []
-for _ in range(3):
+for chunk in (16384, 8192, 4096, 2048):
+  lair_b200._ffi.set_option("batched_chunk", chunk)
+  ts = []
+  for _ in range(3):
     w[...] = h
     t0 = time.perf_counter()
     p, i_ = lair_b200.lapack.getrf_batched(w)
     ts.append(time.perf_counter() - t0)
-t = min(ts)
-print(json.dumps({"probe": "c3 e2e f64, pinned matrices, pageable pivots/info", "matrices": nmat, "ms": [round(x * 1e3, 2) for x in ts],
-                  "mats_per_s": nmat / t, "h2d_GBps": w.nbytes / t * 1e-9, "d2h_GBps": (w.nbytes + p.nbytes + i_.nbytes) / t * 1e-9}), flush=True)
+  t = min(ts)
+  print(json.dumps({"probe": "c3 e2e f64, pinned matrices, pageable pivots/info", "matrices": nmat, "batched_chunk": chunk, "ms": [round(x * 1e3, 2) for x in ts],
+                    "mats_per_s": nmat / t, "h2d_GBps": w.nbytes / t * 1e-9, "d2h_GBps": (w.nbytes + p.nbytes + i_.nbytes) / t * 1e-9}), flush=True)
