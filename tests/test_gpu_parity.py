@@ -107,6 +107,29 @@ def test_batched_ties_singular_nan(lair, dt):
     assert e_ipiv.shape == (0, 32) and e_info.shape == (0,)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("chunk", [256, 1000, 8192])
+def test_batched_host_entry_chunked_pipeline(lair, dt, chunk):
+    """The host-pointer entry pipelines H2D / factor / D2H in chunks of `batched_chunk` matrices and returns pivots and
+    info in one piece afterwards: every chunking, ragged last chunk and the > 64-chunk regrouping included, gives the
+    oracle's bits."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(23)
+    a0 = _rand(rng, (17001, 32, 32), dt)  # chunk 256 -> 67 chunks, regrouped to 64 of 266 with a ragged tail
+    a = a0.copy()
+    old = _ffi.get_option("batched_chunk")
+    _ffi.set_option("batched_chunk", chunk)
+    try:
+        ipiv, info = lair.lapack.getrf_batched(a)
+    finally:
+        _ffi.set_option("batched_chunk", old)
+    ref = a0.copy()
+    piv_o, info_o = oracle.getrf_batched(ref)
+    assert np.array_equal(ipiv, piv_o.astype(np.int32))
+    assert np.array_equal(info, info_o.astype(np.int32))
+    assert np.array_equal(a, ref)
+
+
 # ---- single-CTA small path (C1 shape): bit-exact on standard layouts ------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64, np.complex128])
 @pytest.mark.parametrize("shape", [(1, 1), (2, 2), (7, 7), (33, 33), (100, 100), (128, 128), (40, 17), (17, 40), (128, 3)])
