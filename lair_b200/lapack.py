@@ -158,10 +158,17 @@ def gesv(a: np.ndarray, b: np.ndarray):
 
     Returns (x, singular); x is None when singular (equation.rs:55-57).
     """
+    b = np.asarray(b)
+    if a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("gesv expects a square 2-D matrix")
     n = a.shape[0]
     pfx = _prefix(a)
     if pfx not in "sd":
         raise TypeError("gesv supports f32 and f64")
+    if b.ndim not in (1, 2) or b.shape[0] != n:
+        raise ValueError(f"gesv: b has {b.shape[0] if b.ndim else 0} rows, a has {n}")
+    if b.dtype != a.dtype:  # the C side reinterprets b's bytes as a's scalar type
+        raise TypeError("a and b must have the same scalar type")
     one_d = b.ndim == 1
     b2 = b.reshape(n, 1) if one_d else b
     nrhs = b2.shape[1]
