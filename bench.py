@@ -1,28 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- the hot path's headline benchmark (driver contract, see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4|c2|c3]
 
-Metric (BASELINE.json): getrf f64 GFLOP/s with the 2/3 n^3 convention.  Default workload at
-N=1 is BASELINE configs[1] ("c2"): getrf + getrs, f64, n = 8192, 64 right-hand sides, uniform
-[0,10) synthetic data.  One step = factor A and solve for the 64 right-hand sides;
-flops/step = 2/3 n^3 + 2 n^2 nrhs.
+Metric (BASELINE.json): getrf f64 GFLOP/s with the 2/3 n^3 convention + batched LU matrices/s.
+ONE headline workload at every N (so the driver's 1 -> 8 curve divides like by like): BASELINE configs[3]
+("c4"), a single f64 LU of order n = 65 536 -- on one GPU through lair_b200_dgetrf_dev (34.4 GB + a pristine
+copy fit one 180 GB B200), on N > 1 GPUs through the 1-D block-cyclic NCCL path (lair_b200_dgetrf_mg_dev).
+`scaling` is "strong" everywhere.  One step = restore the matrix from the pristine copy + factor it.
 
 * `value`  : device-resident (inputs already in HBM), CUDA events, max over ranks.
-* `e2e`    : the same step through the public host API (`lair_b200.equation.solve`, i.e. the
-             C ABI's lair_b200_dgesv) with pinned HOST buffers; H2D/D2H inside the timed region.
-* `roofline`: the dominant kernel (DMMA GEMM trailing update), algorithmic flops / its device
-             time measured live with CUDA events on the launching stream (lair_b200_profile_*).
-* `cpu_baseline`: the oracle (C++ restatement of the reference's single-threaded algorithm)
-             on a bounded sample, rank 0, N=1 only.
-* `--impl reference`: times the reference's CPU algorithm (oracle port; the reference is Rust
-             and cannot be built in this image) on the host cores; same JSON shape.
-
-N>1 ranks (torchrun) default to `--workload c4`: ONE f64 LU of order 65536 (BASELINE configs[3]) on
-a 1-D block-cyclic column distribution, NCCL panel/pivot broadcast with lookahead (strong scaling;
-value = 2/3 n^3 / time, also reported as a fraction of N x 37.0 TFLOP/s).  `--workload c2` under
-torchrun runs independent n = 8192 systems per rank (weak scaling, no collective); `--workload c3`
-benches the batched 32x32 path (mats/s), sharded by batch.
+* `e2e`    : the same factorization through the public host API with pinned HOST buffers: H2D of A, getrf, D2H of
+             L\\U and the pivots inside the timed region (N = 1: lair_b200.lapack.getrf -> lair_b200_dgetrf;
+             N > 1: each rank's column slab up, lair_b200.multigpu.getrf_mg, the slab of L\\U back down).
+* `roofline`: the dominant kernel (DMMA GEMM trailing update): algorithmic flops / its device time measured live
+             with CUDA events on the launching stream (lair_b200_profile_*), against the measured 37.0 TFLOP/s.
+* `cpu_baseline`: the oracle (C++ restatement of the reference's single-threaded algorithm) on a bounded sample,
+             rank 0, N = 1 only.
+* extra keys in the SAME line -- the other BASELINE configs, each with its own roofline / e2e:
+     N = 1: `c2` (getrf + getrs f64 n = 8192, 64 RHS; getrf e2e with pinned AND pageable buffers),
+            `c3_f64`, `c3_f32` (10^6 x 32x32 batched LU: mats/s, GB/s, fraction of the measured HBM copy bandwidth),
+            `c5a` (262 144 x 1024 f32), `c5b` (16 384^2 f64) with the device-side backward error;
+     N > 1: `c3_f64`, `c3_f32` with the batch sharded over the ranks (no collective).
+* `--impl reference`: times the reference's CPU algorithm (oracle port; the reference is Rust and cannot be built
+             in this image) on the host cores; same JSON shape.
+`--workload c2` / `--workload c3` print those workloads as stand-alone lines (ncu captures, tuning).
 """
 from __future__ import annotations
 
@@ -44,6 +46,8 @@ N_C2, NRHS_C2 = 8192, 64
 FP64_PEAK_TFLOPS = 37.0   # measured on this pool's B200: DMMA m8n8k4 issue-rate microbench,
                           # profiles/r1_microbench_fp64_peak.jsonl (= 148 SMs x 64 FMA/clk x 1.965 GHz);
                           # cuBLAS DGEMM 8192^3 reaches 35.5 on the same box (profiles/r1_probe_first_contact.jsonl)
+FP64_PEAK_SOURCE = ("FP64 DMMA issue-rate microbench on this pool's B200 (profiles/r1_microbench_fp64_peak.jsonl); "
+                    "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM reaches 35.5; nominal 40 is reported beside it")
 
 
 def _peaks():
@@ -153,13 +157,15 @@ def _barrier(world: int):
 # from the committed `ncu --set full` capture (profiles/r1c_ncu_full_metrics.txt): f32 4.263 + 4.170 GB
 # against 8.32 GB algorithmic, f64 9.053 + 8.268 GB against 16.51 GB.
 NCU_TRAFFIC_C3 = {"f32": 4262975000 + 4169763000, "f64": 9052583000 + 8267601000}
+NCU_TRAFFIC_C3_SOURCE = "from capture profiles/r1c_ncu_full_metrics.txt (ncu --set full of the batched kernel at this size; not measured by this run)"
+BATCHED_KERNEL_NAME = "batched_lu32 (batched_lu5.cu / batched_lu4.cu, chosen by batched_cfg)"
 # same counters for the largest DMMA GEMM launch of the c2 step (7808 x 7680 x 128; profiles/r1_final_ncu_full_metrics.txt):
 # 498.7 MB read + 427.7 MB written against 959 MB of algorithmic C read + write (A and B panels stay in L2).
 NCU_TRAFFIC_C2_GEMM = 498718976 + 427666176
 
 
 def cpu_sample_c2(n_sample: int = 4096, nrhs: int = NRHS_C2, seed: int = 1):
-    """The oracle on a bounded sample of the c2 workload: n_sample x n_sample f64 getrf + nrhs
+    """The oracle on a bounded sample of the dense workload: n_sample x n_sample f64 getrf + nrhs
     single-RHS getrs calls (the reference has no multi-RHS getrs), ONE core."""
     import oracle
     rng = np.random.default_rng(seed)
@@ -190,11 +196,11 @@ def run_reference(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": "getrf_f64_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10)",
-        "config": {"workload": (f"c2 getrf+getrs f64 n={N_C2} nrhs={NRHS_C2}" if world == 1 else f"c4 getrf f64 n={args.n}") +
-                               f" (bounded sample: n={ref_n} getrf + {NRHS_C2} getrs; the reference is O(n^3) scalar code, "
-                               "n=8192 would take minutes and n=65536 ~35 h on one core)", "inputs": "host"},
-        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10)",
+        "config": {"workload": f"c4: single getrf f64 n={args.n} (bounded sample: n={ref_n} getrf + {NRHS_C2} getrs on ONE host core; "
+                               "the reference is O(n^3) single-threaded scalar code, n=65536 would take ~35 h)", "inputs": "host"},
+        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,20 +208,33 @@ def run_reference(args, rank: int, world: int):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_c2(args, rank: int, world: int, local: int):
+def _time_host_call(fn, steps: int, restore=None) -> float:
+    """Seconds per call of a host-API entry (wall clock: the call returns when the result is back in host memory)."""
+    t = 0.0
+    for _ in range(steps):
+        if restore:
+            restore()
+        t0 = time.perf_counter()
+        fn()
+        t += time.perf_counter() - t0
+    return t / steps
+
+
+def measure_c2(args, rank: int, world: int, local: int, sampler=None) -> dict:
+    """BASELINE configs[1]: getrf + getrs, f64, n = 8192, 64 right-hand sides, one system per rank."""
     import torch
     from lair_b200 import _ffi
     import lair_b200
 
     L = _ffi.lib()
-    _ffi.check(L.lair_b200_init(local))
     n, nrhs = N_C2, NRHS_C2
     flops_step = 2.0 / 3.0 * n ** 3 + 2.0 * n * n * nrhs
     stream = torch.cuda.current_stream().cuda_stream
+    steps = args.steps
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1 + rank)
-    ncopies = max(1, min(args.steps, 12))
+    ncopies = max(1, min(steps, 12))
     a0 = torch.rand(n, n, dtype=torch.float64, device="cuda", generator=gen) * 10
     b0 = torch.rand(n, nrhs, dtype=torch.float64, device="cuda", generator=gen) * 10
     a_bufs = [a0.clone() for _ in range(ncopies)]
@@ -236,29 +255,28 @@ def run_c2(args, rank: int, world: int, local: int):
     for i in range(args.warmup):
         step(i)
     restore()
-    sampler = ClockSampler(local)
     _barrier(world)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     launches0 = _ffi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     _barrier(world)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         if i and i % ncopies == 0:
             restore()  # only when steps > 12 buffers (not in the default run)
         step(i)
     e1.record()
     _barrier(world)
     ms_total = _max_over_ranks(e0.elapsed_time(e1), world)
-    _ffi.check_fault(torch.cuda.current_stream().cuda_stream)  # a timed-out device-side wait would invalidate the run
+    _ffi.check_fault(stream)  # a timed-out device-side wait would invalidate the run
     launches = _ffi.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / args.steps
+    clocks = sampler.stop() if sampler is not None else None
+    ms_step = ms_total / steps
     value = world * flops_step / ms_step * 1e-6  # GFLOP/s, whole job
 
     # correctness of what was timed: residual of the last solved system, on the device
-    x = b_bufs[(args.steps - 1) % ncopies]
+    x = b_bufs[(steps - 1) % ncopies]
     res = float(torch.linalg.norm(a0 @ x - b0) / (torch.linalg.norm(a0) * torch.linalg.norm(x) * n * 2.0 ** -53))
     info_val = int(info.item())
 
@@ -293,71 +311,81 @@ def run_c2(args, rank: int, world: int, local: int):
     gemm = prof["gemm"]
     gemm_tflops = gemm["work"] / gemm["ms"] * 1e-9 if gemm["ms"] > 0 else 0.0
     kernel_share = {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}
+    del a_bufs, b_bufs
 
-    # end to end through the public host API with pinned host buffers
-    e2e = None
+    # end to end through the public host API
+    e2e = e2e_getrf_pinned = e2e_getrf_pageable = None
     if not args.no_e2e:
         a_host = torch.empty(n, n, dtype=torch.float64).pin_memory()
         b_host = torch.empty(n, nrhs, dtype=torch.float64).pin_memory()
         a_host.copy_(a0)
         b_host.copy_(b0)
         a_np, b_np = a_host.numpy(), b_host.numpy()
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(steps, 5))
         lair_b200.equation.solve(a_np, b_np)  # warm-up (allocates the device pool)
         _barrier(world)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            x_host = lair_b200.equation.solve(a_np, b_np)
-        t_e2e = (time.perf_counter() - t0) / e2e_steps
+        box = {}
+        t_e2e = _time_host_call(lambda: box.__setitem__("x", lair_b200.equation.solve(a_np, b_np)), e2e_steps)
         t_e2e = _max_over_ranks(t_e2e * 1e3, world) * 1e-3
         e2e = {"value": world * flops_step / t_e2e * 1e-9, "unit": "GFLOP/s", "ms_per_step": t_e2e * 1e3,
-               "h2d_bytes_per_step": int(a_np.nbytes + b_np.nbytes), "d2h_bytes_per_step": int(x_host.nbytes + 4),
+               "h2d_bytes_per_step": int(a_np.nbytes + b_np.nbytes), "d2h_bytes_per_step": int(box["x"].nbytes + 4),
                "api": "lair_b200.equation.solve -> lair_b200_dgesv (pinned host buffers)"}
+        # the getrf contract itself (getrf.rs:12 overwrites the caller's array): H2D of A, factor, D2H of L\U + pivots
+        gflops_getrf = 2.0 / 3.0 * n ** 3
+        work_pin = torch.empty(n, n, dtype=torch.float64).pin_memory()
+        w_np = work_pin.numpy()
+        w_np[...] = a_np
+        lair_b200.lapack.getrf(w_np)
+        t = _time_host_call(lambda: lair_b200.lapack.getrf(w_np), e2e_steps, restore=lambda: np.copyto(w_np, a_np))
+        t = _max_over_ranks(t * 1e3, world) * 1e-3
+        e2e_getrf_pinned = {"value": world * gflops_getrf / t * 1e-9, "unit": "GFLOP/s", "ms_per_step": t * 1e3,
+                            "h2d_bytes_per_step": int(a_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes + 8 * n + 8),
+                            "api": "lair_b200.lapack.getrf -> lair_b200_dgetrf (pinned host array, factored in place)"}
+        w_page = np.empty((n, n), dtype=np.float64)  # an ordinary ndarray: pageable
+        w_page[...] = a_np
+        lair_b200.lapack.getrf(w_page)
+        t = _time_host_call(lambda: lair_b200.lapack.getrf(w_page), e2e_steps, restore=lambda: np.copyto(w_page, a_np))
+        t = _max_over_ranks(t * 1e3, world) * 1e-3
+        e2e_getrf_pageable = {"value": world * gflops_getrf / t * 1e-9, "unit": "GFLOP/s", "ms_per_step": t * 1e3,
+                              "h2d_bytes_per_step": int(a_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes + 8 * n + 8),
+                              "api": "lair_b200.lapack.getrf -> lair_b200_dgetrf (pageable numpy array, factored in place)"}
+        del a_host, b_host, work_pin, w_page
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        g, tg, ts, sample = cpu_sample_c2(args.ref_n)
-        cpu = {"value": g, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample,
-               "host_cores_available": os.cpu_count()}
-
-    if rank == 0:
-        line = {
-            "metric": "getrf_f64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10), random seed per rank",
-            "config": {"workload": f"c2: getrf+getrs f64 n={n} nrhs={nrhs} per GPU (flops = 2/3 n^3 + 2 n^2 nrhs)",
-                       "l2": "inputs (512 MiB per system, a fresh buffer per step) exceed the 126 MB L2",
-                       "nb": _ffi.get_option("nb") or "auto by remaining size (128 while > 6144 columns remain, then 64)", "sharding": "independent systems per rank, no collective"},
-            "getrf_ms": getrf_ms, "getrs_ms": getrs_ms, "getrf_gflops": 2.0 / 3.0 * n ** 3 / getrf_ms * 1e-6,
-            "residual_scaled": res, "info": info_val,
-            "roofline": {"bound": "tensor", "kernel": "dgemm_minus_kernel (DMMA m8n8k4 trailing update)",
-                         "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": gemm_tflops / FP64_PEAK_TFLOPS,
-                         "peak_source": "FP64 DMMA issue-rate microbench on this pool's B200 (profiles/r1_microbench_fp64_peak.jsonl); "
-                                        "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM reaches 35.5",
-                         "launches": gemm["launches"], "kernel_ms_in_step": gemm["ms"],
-                         "traffic": NCU_TRAFFIC_C2_GEMM if n == 8192 else None,
-                         "traffic_unit": "bytes of the step's largest launch (M x N x K = 7808 x 7680 x 128; "
-                                         "dram__bytes_read.sum + dram__bytes_write.sum), algorithmic C read + write = 959 MB",
-                         "traffic_source": "profiles/r1_final_ncu_full_metrics.txt (ncu --set full capture of that launch)",
-                         "kernel_ms_by_family": kernel_share},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
+    return {
+        "metric": "getrf_f64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10), random seed per rank",
+        "config": {"workload": f"c2: getrf+getrs f64 n={n} nrhs={nrhs} per GPU (flops = 2/3 n^3 + 2 n^2 nrhs)",
+                   "l2": "inputs (512 MiB per system, a fresh buffer per step) exceed the 126 MB L2",
+                   "nb": _ffi.get_option("nb") or "auto by remaining size", "sharding": "independent systems per rank, no collective"},
+        "getrf_ms": getrf_ms, "getrs_ms": getrs_ms, "getrf_gflops": 2.0 / 3.0 * n ** 3 / getrf_ms * 1e-6,
+        "frac_of_fp64_peak": value * 1e-3 / (FP64_PEAK_TFLOPS * world),
+        "residual_scaled": res, "info": info_val,
+        "roofline": {"bound": "tensor", "kernel": "dgemm_minus_kernel (DMMA m8n8k4 trailing update)",
+                     "achieved": gemm_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": gemm_tflops / FP64_PEAK_TFLOPS, "peak_source": FP64_PEAK_SOURCE,
+                     "launches": gemm["launches"], "kernel_ms_in_step": gemm["ms"],
+                     "traffic": NCU_TRAFFIC_C2_GEMM,
+                     "traffic_unit": "bytes of the step's largest launch (M x N x K = 7808 x 7680 x 128; "
+                                     "dram__bytes_read.sum + dram__bytes_write.sum), algorithmic C read + write = 959 MB",
+                     "traffic_source": "from capture profiles/r1_final_ncu_full_metrics.txt (ncu --set full of that launch; not measured by this run)",
+                     "kernel_ms_by_family": kernel_share},
+        "e2e": e2e, "e2e_getrf_pinned": e2e_getrf_pinned, "e2e_getrf_pageable": e2e_getrf_pageable,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
 
 
-def run_c3(args, rank: int, world: int, local: int):
-    """Batched 32x32 LU, 10^6 matrices sharded over the ranks (HBM-bound path)."""
+def measure_c3(args, dtype: str, rank: int, world: int, local: int, sampler=None, cpu: bool = True) -> dict:
+    """BASELINE configs[2]: batched 32x32 LU, 10^6 matrices sharded over the ranks (HBM-bound path)."""
     import torch
-    from lair_b200 import _ffi
+    from lair_b200 import _ffi, sharding
     import lair_b200
 
     L = _ffi.lib()
-    _ffi.check(L.lair_b200_init(local))
     peaks, peak_src = _peaks()
-    dt, pfx, bpm = (torch.float64, "d", 16512) if args.dtype == "f64" else (torch.float32, "s", 8320)
+    dt, pfx, bpm = (torch.float64, "d", 16512) if dtype == "f64" else (torch.float32, "s", 8320)
     total = 1_000_000
-    batch = total // world  # per-rank shard (weak in the sense of the contract: fixed per-GPU work is total/N here)
+    _, batch = sharding.batch_slice(total, rank, world)  # contiguous slices of the batch, no collective
     stream = torch.cuda.current_stream().cuda_stream
     gen = torch.Generator(device="cuda")
     gen.manual_seed(3 + rank)
@@ -366,20 +394,21 @@ def run_c3(args, rank: int, world: int, local: int):
     ipiv = torch.empty(batch, 32, dtype=torch.int32, device="cuda")
     info = torch.empty(batch, dtype=torch.int32, device="cuda")
     fn = getattr(L, f"lair_b200_{pfx}getrf_batched_dev")
+    steps = max(3, min(args.steps, 10))
 
     def step():
         _ffi.check(fn(batch, 32, a.data_ptr(), ipiv.data_ptr(), info.data_ptr(), stream))
 
-    for _ in range(args.warmup):
+    for _ in range(max(3, args.warmup)):
+        a.copy_(a0)
         step()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     # time each step separately so the restore copy (a <- a0) stays outside the timed region
     ms_total = 0.0
     launches0 = _ffi.launch_count()
     _barrier(world)
-    for _ in range(args.steps):
+    for _ in range(steps):
         a.copy_(a0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -391,10 +420,27 @@ def run_c3(args, rank: int, world: int, local: int):
     _barrier(world)
     ms_total = _max_over_ranks(ms_total, world)
     launches = _ffi.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / args.steps
-    value = batch * world / ms_step * 1e3
-    gbs = batch * bpm / ms_step * 1e-6
+    clocks = sampler.stop() if sampler is not None else None
+    ms_step = ms_total / steps
+    value = total / ms_step * 1e3
+    gbs = batch * bpm / ms_step * 1e-6  # per GPU
+    # what was timed is right: P A = L U on a sample, on the device in f64; no singular flags
+    ns = min(batch, 4096)
+    LU = a[:ns].double()
+    Lm = torch.tril(LU, -1) + torch.eye(32, dtype=torch.float64, device="cuda")
+    rec = Lm @ torch.triu(LU)
+    pv = ipiv[:ns].cpu().numpy()
+    perm = np.tile(np.arange(32), (ns, 1))
+    rows = np.arange(ns)
+    for j in range(32):
+        p = pv[:, j]
+        tmp = perm[rows, j].copy()
+        perm[rows, j] = perm[rows, p]
+        perm[rows, p] = tmp
+    PA = torch.gather(a0[:ns].double(), 1, torch.from_numpy(perm).cuda()[:, :, None].expand(-1, -1, 32))
+    eps = 2.0 ** -53 if dtype == "f64" else 2.0 ** -24
+    be = float((torch.linalg.norm((PA - rec).reshape(ns, -1), dim=1) / (32 * eps * torch.linalg.norm(PA.reshape(ns, -1), dim=1))).max())
+    n_singular = int((info >= 0).sum().item())
     e2e = None
     if not args.no_e2e:
         eb = min(batch, 200_000)
@@ -405,41 +451,100 @@ def run_c3(args, rank: int, world: int, local: int):
         work = work_t.numpy()
         work[...] = h_np
         lair_b200.lapack.getrf_batched(work)
-        reps = 3
-        t = 0.0
-        for _ in range(reps):
-            work[...] = h_np
-            t0 = time.perf_counter()
-            p, i_ = lair_b200.lapack.getrf_batched(work)  # H2D of the batch, factorization, D2H of L\U + pivots + info
-            t += time.perf_counter() - t0
-        t /= reps
+        box = {}
+        t = _time_host_call(lambda: box.__setitem__("r", lair_b200.lapack.getrf_batched(work)), 3, restore=lambda: np.copyto(work, h_np))
+        t = _max_over_ranks(t * 1e3, world) * 1e-3
+        p, i_ = box["r"]  # H2D of the batch, factorization, D2H of L\U + pivots + info
         e2e = {"value": eb * world / t, "unit": "mats/s", "h2d_bytes_per_step": int(h_np.nbytes),
-               "d2h_bytes_per_step": int(h_np.nbytes + p.nbytes + i_.nbytes), "sample": f"{eb} matrices per call"}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+               "d2h_bytes_per_step": int(h_np.nbytes + p.nbytes + i_.nbytes), "sample": f"{eb} matrices per call per rank",
+               "api": f"lair_b200.lapack.getrf_batched -> lair_b200_{pfx}getrf_batched (pinned host buffers)"}
+        del host, work_t
+    cpu_b = None
+    if cpu and rank == 0 and world == 1 and not args.no_cpu:
         import oracle
         smp = a0[:min(batch, args.ref_batch)].cpu().numpy()
         t0 = time.perf_counter()
         oracle.getrf_batched(smp)
         t = time.perf_counter() - t0
-        cpu = {"value": len(smp) / t, "unit": "mats/s", "cores": 1, "kind": "port",
-               "sample": f"{len(smp)} matrices of the same batch ({t:.1f} s), 1 thread"}
-    if rank == 0:
-        line = {
-            "metric": "batched_lu32_mats_per_s", "value": value, "unit": "mats/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic uniform[0,10)",
-            "config": {"workload": f"c3: batched getrf {args.dtype} 10^6 x 32x32, batch sharded over ranks",
-                       "l2": "per-rank input exceeds L2 at N<=4; restore copy outside the timed region"},
-            "roofline": {"bound": "hbm", "kernel": "batched_lu32_v6_f32 / _f64 (batched_lu4.cu)", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src,
-                         "traffic": NCU_TRAFFIC_C3[args.dtype] if batch == 1_000_000 else None,
-                         "traffic_unit": "bytes per launch of 10^6 matrices (dram__bytes_read.sum + dram__bytes_write.sum)",
-                         "traffic_source": "profiles/r1c_ncu_full_metrics.txt (ncu --set full capture of this kernel at this size)",
-                         "algorithmic_bytes_per_launch": int(batch * bpm)},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
+        cpu_b = {"value": len(smp) / t, "unit": "mats/s", "cores": 1, "kind": "port",
+                 "sample": f"{len(smp)} matrices of the same batch ({t:.1f} s), 1 thread"}
+    return {
+        "metric": "batched_lu32_mats_per_s", "value": value, "unit": "mats/s", "n_gpus": world, "steps": steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic uniform[0,10)",
+        "config": {"workload": f"c3: batched getrf {dtype} 10^6 x 32x32, batch sharded over ranks ({batch} per rank, no collective)",
+                   "l2": "per-rank input exceeds L2 at N<=4; restore copy outside the timed region",
+                   "batched_cfg": _ffi.get_option("batched_cfg")},
+        "mats_per_s_per_gpu": value / world, "backward_error_max_sample": be, "singular_flags": n_singular,
+        "roofline": {"bound": "hbm", "kernel": BATCHED_KERNEL_NAME, "achieved": gbs, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src,
+                     "traffic": NCU_TRAFFIC_C3.get(dtype) if batch == 1_000_000 else None,
+                     "traffic_unit": "bytes per launch of 10^6 matrices (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "traffic_source": NCU_TRAFFIC_C3_SOURCE,
+                     "algorithmic_bytes_per_launch": int(batch * bpm), "algorithmic_bytes_per_matrix": bpm},
+        "cpu_baseline": cpu_b, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
+def measure_c5(args, which: str) -> dict:
+    """BASELINE configs[4]: tall-skinny f32 262 144 x 1024 (c5a, panel-dominated) and f64 n = 16 384 (c5b), one GPU."""
+    import torch
+    from lair_b200 import _ffi
+    import devcheck
+
+    L = _ffi.lib()
+    m, n, dt, pfx = (262144, 1024, torch.float32, "s") if which == "c5a" else (16384, 16384, torch.float64, "d")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5 if which == "c5a" else 6)
+    a0 = torch.rand(m, n, dtype=dt, device="cuda", generator=gen) * 10
+    a = torch.empty_like(a0)
+    k = min(m, n)
+    ipiv = torch.empty(k, dtype=torch.int32, device="cuda")
+    info = torch.empty(1, dtype=torch.int32, device="cuda")
+    fn = getattr(L, f"lair_b200_{pfx}getrf_dev")
+    stream = torch.cuda.current_stream().cuda_stream
+    steps = max(2, min(args.steps, 5))
+    ts = []
+    for i in range(3 + steps):
+        a.copy_(a0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _ffi.check(fn(m, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    _ffi.check_fault(stream)
+    ms = float(np.mean(ts))
+    # live per-family times of one more factorization
+    a.copy_(a0)
+    torch.cuda.synchronize()
+    _ffi.profile_begin()
+    _ffi.check(fn(m, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream))
+    prof = _ffi.profile_end()
+    flops = m * n * n - n ** 3 / 3.0
+    be = devcheck.backward_error_dev(a0, a, ipiv)
+    esz = 4 if dt == torch.float32 else 8
+    out = {"workload": f"{which}: getrf {'f32' if esz == 4 else 'f64'} {m} x {n}, one GPU (flops = m n^2 - n^3/3)", "ms": ms, "steps": steps, "warmup": 3,
+           "gflops": flops / ms * 1e-6, "backward_error": be, "backward_error_bound": 0.5, "info": int(info.item()),
+           "kernel_ms_by_family": {kk: round(v["ms"], 3) for kk, v in prof.items() if v["launches"]}}
+    if which == "c5b":
+        out["frac_of_fp64_peak"] = flops / ms * 1e-9 / FP64_PEAK_TFLOPS
+        g = prof["gemm"]
+        out["roofline"] = {"bound": "tensor", "kernel": "dgemm_minus_kernel", "achieved": g["work"] / g["ms"] * 1e-9 if g["ms"] > 0 else 0.0,
+                           "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": (g["work"] / g["ms"] * 1e-9 / FP64_PEAK_TFLOPS) if g["ms"] > 0 else 0.0, "traffic": None}
+    else:
+        peaks, peak_src = _peaks()
+        pn = prof["panel"]
+        # panel kernels: every column block of the panel is read and written once per launch (algorithmic 2 * rows * w * sizeof)
+        out["roofline"] = {"bound": "hbm", "kernel": "panel kernels (panel_blocked.cu / panel.cu)", "achieved": pn["work"] / pn["ms"] * 1e-6 if pn["ms"] > 0 else 0.0,
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (pn["work"] / pn["ms"] * 1e-6 / peaks["hbm_gbs"]) if pn["ms"] > 0 else 0.0,
+                           "peak_source": peak_src, "traffic": None,
+                           "note": "latency-bound (one dependent arg-max per column), reported against HBM as SURVEY 8(d) asks"}
+    del a0, a
+    torch.cuda.empty_cache()
+    return out
 
 
 def _host_mem_available() -> int:
@@ -461,15 +566,135 @@ def _host_mem_available() -> int:
     return max(avail, 0)
 
 
-def run_c4(args, rank: int, world: int, local: int):
+def run_c4_single(args, rank: int, world: int, local: int) -> dict:
+    """The headline workload on ONE GPU: a single f64 LU of order n (65 536: 34.4 GB + a pristine copy) through
+    lair_b200_dgetrf_dev -- the N = 1 point of the strong-scaling curve."""
+    import torch
+    from lair_b200 import _ffi
+    import lair_b200
+
+    L = _ffi.lib()
+    n = args.n
+    stream = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    a0 = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    for r0 in range(0, n, 8192):  # generated by row blocks: torch.rand(...) * 10 would need a second n x n temporary
+        r1 = min(n, r0 + 8192)
+        a0[r0:r1] = torch.rand(r1 - r0, n, dtype=torch.float64, device="cuda", generator=gen) * 10
+    a = torch.empty_like(a0)
+    ipiv = torch.empty(n, dtype=torch.int32, device="cuda")
+    info = torch.empty(1, dtype=torch.int32, device="cuda")
+    flops = 2.0 / 3.0 * n ** 3
+
+    def step():
+        a.copy_(a0)  # in-place factorization: restore from the pristine copy (inside the timed region, ~0.3 % of a step)
+        _ffi.check(L.lair_b200_dgetrf_dev(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream))
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = _ffi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    _ffi.check_fault(stream)
+    launches = _ffi.launch_count() - launches0
+    clocks = sampler.stop()
+    value = flops / ms_step * 1e-6
+
+    # size-independent parity property: || (P A - L U) x || / (||A|| ||x|| n eps) for a random x
+    torch.manual_seed(99)
+    x = torch.rand(n, dtype=torch.float64, device="cuda")
+    y = torch.zeros(n, dtype=torch.float64, device="cuda")
+    z = torch.zeros(n, dtype=torch.float64, device="cuda")
+    w = a0 @ x
+    bs = 4096
+    for c0 in range(0, n, bs):  # y = U x
+        c1 = min(n, c0 + bs)
+        y[:c0] += a[:c0, c0:c1] @ x[c0:c1]
+        y[c0:c1] += torch.triu(a[c0:c1, c0:c1]) @ x[c0:c1]
+    for c0 in range(0, n, bs):  # z = L y
+        c1 = min(n, c0 + bs)
+        z[c1:] += a[c1:, c0:c1] @ y[c0:c1]
+        z[c0:c1] += (torch.tril(a[c0:c1, c0:c1], -1) + torch.eye(c1 - c0, dtype=torch.float64, device="cuda")) @ y[c0:c1]
+    import devcheck
+    perm = torch.from_numpy(devcheck.perm_from_pivots(ipiv.cpu().numpy(), n)).cuda()
+    resid = float(torch.linalg.norm(w[perm] - z) / (torch.linalg.norm(a0) * torch.linalg.norm(x) * n * 2.0 ** -53))
+    info_val = int(info.item())
+
+    # live per-kernel-family timing of one more factorization (serialises the streams)
+    a.copy_(a0)
+    torch.cuda.synchronize()
+    _ffi.profile_begin()
+    _ffi.check(L.lair_b200_dgetrf_dev(n, n, a.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), stream))
+    prof = _ffi.profile_end()
+    gemm = prof["gemm"]
+    gemm_tflops = gemm["work"] / gemm["ms"] * 1e-9 if gemm["ms"] > 0 else 0.0
+    kernel_share = {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}
+    del a
+    torch.cuda.empty_cache()
+
+    # end to end: the getrf contract through the host API -- H2D of A, factor, D2H of L\U and the pivots
+    e2e = None
+    if not args.no_e2e:
+        nbytes = n * n * 8
+        if nbytes * 1.2 < _host_mem_available():
+            host = torch.empty(n, n, dtype=torch.float64).pin_memory()
+            h_np = host.numpy()
+            e2e_steps = 2
+
+            def restore():
+                host.copy_(a0)  # untimed: the pristine matrix back into the pinned host array
+                torch.cuda.synchronize()
+
+            restore()
+            lair_b200.lapack.getrf(h_np)  # warm-up: sizes the library's device pool
+            t = _time_host_call(lambda: lair_b200.lapack.getrf(h_np), e2e_steps, restore=restore)
+            e2e = {"value": flops / t * 1e-9, "unit": "GFLOP/s", "ms_per_step": t * 1e3, "steps": e2e_steps,
+                   "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes + 8 * n + 8),
+                   "api": "lair_b200.lapack.getrf -> lair_b200_dgetrf (pinned host array factored in place: H2D of A, getrf, D2H of L\\U + pivots)"}
+            del host
+        else:
+            e2e = {"value": None, "unit": "GFLOP/s", "skipped": f"{nbytes / 2**30:.0f} GiB pinned host array vs {_host_mem_available() / 2**30:.0f} GiB free",
+                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    del a0
+    torch.cuda.empty_cache()
+
+    return {
+        "metric": "getrf_f64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10), generated on device",
+        "config": {"workload": f"c4: single getrf f64 n={n} on 1 GPU (lair_b200_dgetrf_dev; the same matrix order the N>1 lines distribute)",
+                   "l2": f"matrix {n * n * 8 / 2**30:.1f} GiB exceeds L2; restored from a pristine copy inside the timed region",
+                   "flops": "2/3 n^3", "nb": _ffi.get_option("nb") or "auto by remaining size"},
+        "frac_of_aggregate_fp64_peak": value * 1e-3 / FP64_PEAK_TFLOPS, "aggregate_fp64_peak_tflops": FP64_PEAK_TFLOPS,
+        "frac_of_nominal_40": value * 1e-3 / 40.0,
+        "residual_scaled_PA_minus_LU_times_x": resid, "info": info_val,
+        "roofline": {"bound": "tensor", "kernel": "dgemm_minus_kernel (DMMA m8n8k4 trailing update)", "achieved": gemm_tflops,
+                     "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm_tflops / FP64_PEAK_TFLOPS, "peak_source": FP64_PEAK_SOURCE,
+                     "launches": gemm["launches"], "kernel_ms_in_step": gemm["ms"], "traffic": None,
+                     "traffic_note": "per-launch DRAM bytes of this kernel: see c2.roofline (ncu capture)",
+                     "kernel_ms_by_family": kernel_share},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
+def run_c4(args, rank: int, world: int, local: int) -> dict:
     """One large f64 LU, 1-D block-cyclic columns over the ranks, NCCL panel broadcast + lookahead
-    (BASELINE configs[3]; n = 65536 unless --n).  Strong scaling: the matrix is fixed, ranks split it."""
+    (BASELINE configs[3]; n = 65536 unless --order).  Strong scaling: the matrix is fixed, ranks split it."""
     import torch
     import torch.distributed as dist
     from lair_b200 import _ffi, multigpu, sharding
 
     L = _ffi.lib()
-    _ffi.check(L.lair_b200_init(local))
     multigpu.init()
     n, nb = args.n, args.nb
     lcols = sharding.local_cols(n, nb, rank, world)
@@ -480,7 +705,7 @@ def run_c4(args, rank: int, world: int, local: int):
     flops = 2.0 / 3.0 * n ** 3
 
     def step():
-        a.copy_(a0)  # in-place factorization: restore the slab (6 ms of 5 s at n = 65536; inside the timed region)
+        a.copy_(a0)  # in-place factorization: restore the slab (6 ms of 1 s at n = 65536; inside the timed region)
         return multigpu.getrf_mg(a, n, nb)
 
     for _ in range(args.warmup):
@@ -535,77 +760,82 @@ def run_c4(args, rank: int, world: int, local: int):
             pw[i], pw[p] = pw[p], pw[i]
     resid = float(np.linalg.norm(pw - z.cpu().numpy()) / (float(anorm2.sqrt()) * float(torch.linalg.norm(x)) * n * 2.0 ** -53))
 
-    # end to end through the public API (lair_b200.multigpu.getrf_mg): every step uploads the rank's
-    # column slab from pinned host memory and reads the pivots + info back.  Skipped (null, with the
-    # reason) when the slabs of all ranks would not comfortably fit the host's free memory.
+    # end to end through the public API (lair_b200.multigpu.getrf_mg): every step uploads the rank's column slab
+    # from pinned host memory, factors, and brings the slab of L\U, the pivots and info back to the host.
+    # Skipped (null, with the reason) when the slabs of all ranks would not comfortably fit the host's free memory.
     e2e = None
     if not args.no_e2e:
         slab_bytes = a0.numel() * 8
         avail = _host_mem_available()
-        fits = torch.tensor([1 if slab_bytes * world * 2 < avail else 0], device="cuda")
+        fits = torch.tensor([1 if slab_bytes * world * 2.4 < avail else 0], device="cuda")  # an input and an output slab per rank
         dist.all_reduce(fits, op=dist.ReduceOp.MIN)
         if int(fits.item()) == 1:
             host = torch.empty(a0.shape, dtype=torch.float64).pin_memory()
+            host_out = torch.empty(a0.shape, dtype=torch.float64).pin_memory()
             host.copy_(a0)
             e2e_steps = 2
 
             def e2e_step():
                 a.copy_(host, non_blocking=True)
                 piv, inf = multigpu.getrf_mg(a, n, nb)
-                return piv.cpu(), int(inf.cpu().item())
+                host_out.copy_(a, non_blocking=True)
+                piv_h, inf_h = piv.cpu(), int(inf.cpu().item())  # synchronises: the slab copy above is on the same stream
+                return piv_h, inf_h
 
             e2e_step()
             _barrier(world)
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                piv_h, _ = e2e_step()
+                piv_h, _inf = e2e_step()
             _barrier(world)
             t_e2e = _max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3, world) * 1e-3
-            e2e = {"value": flops / t_e2e * 1e-9, "unit": "GFLOP/s", "ms_per_step": t_e2e * 1e3,
-                   "h2d_bytes_per_step": int(slab_bytes) * world, "d2h_bytes_per_step": int(piv_h.numel() * 4 + 4) * world,
-                   "api": "lair_b200.multigpu.getrf_mg (per-rank column slab from pinned host memory; pivots + info read back)"}
-            del host
+            e2e = {"value": flops / t_e2e * 1e-9, "unit": "GFLOP/s", "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+                   "h2d_bytes_per_step": int(slab_bytes) * world, "d2h_bytes_per_step": int(slab_bytes + piv_h.numel() * 4 + 4) * world,
+                   "api": "lair_b200.multigpu.getrf_mg (per-rank column slab from pinned host memory; the slab of L\\U + pivots + info read back)"}
+            del host, host_out
         else:
             e2e = {"value": None, "unit": "GFLOP/s", "skipped": f"{world} x {slab_bytes / 2**30:.1f} GiB of pinned slabs "
                    f"vs {avail / 2**30:.0f} GiB of free host memory", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-
-    if rank == 0:
-        peak = FP64_PEAK_TFLOPS * world
-        line = {
-            "metric": "getrf_f64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10), generated per rank on device",
-            "config": {"workload": f"c4: single getrf f64 n={n}, 1-D block-cyclic columns nb={nb} over {world} GPUs, "
-                                   "NCCL panel+pivot broadcast with one block of lookahead",
-                       "l2": f"per-rank slab {a0.numel() * 8 / 2**30:.1f} GiB exceeds L2; slab restored from a pristine copy inside the timed region",
-                       "flops": "2/3 n^3"},
-            "frac_of_aggregate_fp64_peak": value * 1e-3 / peak, "aggregate_fp64_peak_tflops": peak,
-            "residual_scaled_PA_minus_LU_times_x": resid, "info": int(info.item()),
-            "roofline": {"bound": "tensor", "kernel": "dgemm_minus_kernel (DMMA m8n8k4 trailing update)", "achieved": value * 1e-3 / world,
-                         "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": value * 1e-3 / peak,
-                         "note": "whole-factorization FLOP/s per GPU (the kernel-only figure is reported by the N=1 line)", "traffic": None},
-            "cpu_baseline": None,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
+    del a0, a
+    torch.cuda.empty_cache()
     multigpu.finalize()
+
+    peak = FP64_PEAK_TFLOPS * world
+    return {
+        "metric": "getrf_f64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic uniform[0,10), generated per rank on device",
+        "config": {"workload": f"c4: single getrf f64 n={n}, 1-D block-cyclic columns nb={nb} over {world} GPUs, "
+                               "NCCL panel+pivot broadcast with one block of lookahead",
+                   "l2": f"per-rank slab {n * lcols * 8 / 2**30:.1f} GiB exceeds L2; slab restored from a pristine copy inside the timed region",
+                   "flops": "2/3 n^3"},
+        "frac_of_aggregate_fp64_peak": value * 1e-3 / peak, "aggregate_fp64_peak_tflops": peak,
+        "frac_of_nominal_40": value * 1e-3 / (40.0 * world),
+        "residual_scaled_PA_minus_LU_times_x": resid, "info": int(info.item()),
+        "roofline": {"bound": "tensor", "kernel": "dgemm_minus_kernel (DMMA m8n8k4 trailing update)", "achieved": value * 1e-3 / world,
+                     "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": value * 1e-3 / peak, "peak_source": FP64_PEAK_SOURCE,
+                     "note": "whole-factorization FLOP/s per GPU (the kernel-only figure is reported by the N=1 line)", "traffic": None},
+        "cpu_baseline": None,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lair_b200", choices=["lair_b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4"],
-                    help="default: c2 on one GPU, c4 (one n=65536 LU distributed over the ranks) on several")
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4"],
+                    help="default c4: one n=65536 LU (single GPU at N=1, distributed over the ranks at N>1) + the other configs as extra keys")
     ap.add_argument("--order", dest="n", type=int, default=65536, help="matrix order n of the c4 workload")
     ap.add_argument("--block", dest="nb", type=int, default=256, help="block-cyclic block width of the c4 workload")
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
-    ap.add_argument("--ref-batch", type=int, default=1_000_000, help="matrices in the CPU (oracle) leg of the c3 workload")
+    ap.add_argument("--ref-batch", type=int, default=100_000, help="matrices in the CPU (oracle) leg of the c3 workload")
     ap.add_argument("--ref-n", type=int, default=4096, help="sample size of the CPU (oracle) leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="c4: skip the c2 / c3 / c5 extra keys")
     ap.add_argument("--ncu-step", action="store_true",
                     help="c2: after the timed region run ONE more step between cudaProfilerStart/Stop "
                          "(for `ncu --profile-from-start off`; numbers printed by such a run are not bench values)")
@@ -618,18 +848,40 @@ def main():
         world = int(os.environ.get("WORLD_SIZE", "1"))
         run_reference(args, rank, world)
         return
-    if args.workload is None:
-        args.workload = "c2" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "c4"
-    rank, world, local = _dist_setup(args.gpus, force=(args.workload == "c4"))
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, world, local = _dist_setup(args.gpus, force=(args.workload == "c4" and world_env > 1))
+    from lair_b200 import _ffi
+    _ffi.check(_ffi.lib().lair_b200_init(local))
     try:
         if args.workload == "c2":
-            run_c2(args, rank, world, local)
+            line = measure_c2(args, rank, world, local, ClockSampler(local) if rank == 0 else None)
+            if rank == 0 and world == 1 and not args.no_cpu:
+                g, tg, ts, sample = cpu_sample_c2(args.ref_n)
+                line["cpu_baseline"] = {"value": g, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample, "host_cores_available": os.cpu_count()}
         elif args.workload == "c3":
-            run_c3(args, rank, world, local)
+            line = measure_c3(args, args.dtype, rank, world, local, ClockSampler(local) if rank == 0 else None)
+        elif world == 1:
+            line = run_c4_single(args, rank, world, local)
+            if not args.no_extras:
+                line["c2"] = measure_c2(args, rank, world, local)
+                line["c3_f64"] = measure_c3(args, "f64", rank, world, local)
+                line["c3_f32"] = measure_c3(args, "f32", rank, world, local)
+                line["c5a"] = measure_c5(args, "c5a")
+                line["c5b"] = measure_c5(args, "c5b")
+            if not args.no_cpu:
+                g, tg, ts, sample = cpu_sample_c2(args.ref_n)
+                line["cpu_baseline"] = {"value": g, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample, "host_cores_available": os.cpu_count()}
+            else:
+                line["cpu_baseline"] = None
         else:
-            run_c4(args, rank, world, local)
+            line = run_c4(args, rank, world, local)
+            if not args.no_extras:
+                line["c3_f64"] = measure_c3(args, "f64", rank, world, local, cpu=False)
+                line["c3_f32"] = measure_c3(args, "f32", rank, world, local, cpu=False)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     finally:
-        if world > 1 or args.workload == "c4":
+        if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
 

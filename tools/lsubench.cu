@@ -11,10 +11,10 @@ using u64 = unsigned long long;
 
 enum Op { LDS128_BCAST, LDS128_2ADDR, LDS128_FULL, LDS64_16ADDR, LDS32_BCAST, STS128_1LANE, STS128_2LANE, STS128_FULL,
           STS128_PREDOFF, STS64_16LANE, REDUX_MAX, VOTE_BALLOT, SHFL_IDX, LDS_BCAST_PLUS_FFMA, LDS_BCAST_PLUS_DFMA, PAIR_STS1_LDSB,
-          FFMA2_ONLY, DFMA_ONLY, STS32_1LANE, STS64_1LANE, STS32_FULL, LDS64_BCAST, SHFL_INDEP, REDUX_INDEP, SEL_ONLY, NOPS };
+          FFMA2_ONLY, DFMA_ONLY, STS32_1LANE, STS64_1LANE, STS32_FULL, LDS64_BCAST, SHFL_INDEP, REDUX_INDEP, SEL_ONLY, SHFL_REGLANE, SHFL_VARLANE, SHFL_REG_PLUS_FFMA2, NOPS };
 static const char* kNames[] = {"lds128_bcast", "lds128_2addr", "lds128_full(4wf)", "lds64_16addr", "lds32_bcast", "sts128_1lane", "sts128_2lane",
                                "sts128_full(4wf)", "sts128_pred_off", "sts64_16lane", "redux_max_u32", "vote_ballot", "shfl_idx",
-                               "lds128_bcast+4ffma2", "lds128_bcast+2dfma", "sts128_1lane+lds128_bcast", "ffma2_only", "dfma_only", "sts32_1lane", "sts64_1lane", "sts32_full", "lds64_bcast", "shfl_idx_indep", "redux_indep", "sel_only"};
+                               "lds128_bcast+4ffma2", "lds128_bcast+2dfma", "sts128_1lane+lds128_bcast", "ffma2_only", "dfma_only", "sts32_1lane", "sts64_1lane", "sts32_full", "lds64_bcast", "shfl_idx_indep", "redux_indep", "sel_only", "shfl_idx_reg_uniform_lane", "shfl_idx_per_lane_src", "shfl_reg_lane+2ffma2"};
 
 template <int OP>
 __global__ void __launch_bounds__(256) bench(unsigned* out, long long* cyc, int iters, int zero) {
@@ -105,6 +105,20 @@ __global__ void __launch_bounds__(256) bench(unsigned* out, long long* cyc, int 
                 asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"((unsigned)x + u), "r"(u & 31));
                 acc ^= r;
             }
+            if (OP == SHFL_REGLANE || OP == SHFL_REG_PLUS_FFMA2) {
+                unsigned r;
+                asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"((unsigned)x + u), "r"(zero + 7));
+                acc ^= r;
+            }
+            if (OP == SHFL_VARLANE) {
+                unsigned r;
+                asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"((unsigned)x + u), "r"((lane * 5 + zero) & 31));
+                acc ^= r;
+            }
+            if (OP == SHFL_REG_PLUS_FFMA2) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(f0) : "l"(fm));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(f1) : "l"(fm));
+            }
             if (OP == REDUX_INDEP) {
                 unsigned r;
                 asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"((unsigned)x + u));
@@ -194,5 +208,8 @@ int main() {
     sweep<LDS64_BCAST>(out, cyc, hcyc);
     sweep<SHFL_INDEP>(out, cyc, hcyc);
     sweep<REDUX_INDEP>(out, cyc, hcyc);
+    sweep<SHFL_REGLANE>(out, cyc, hcyc);
+    sweep<SHFL_VARLANE>(out, cyc, hcyc);
+    sweep<SHFL_REG_PLUS_FFMA2>(out, cyc, hcyc);
     return 0;
 }
