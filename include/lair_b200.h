@@ -171,6 +171,12 @@ LAIR_B200_API int lair_b200_sgemm_minus_dev(int64_t m, int64_t n, int64_t k, con
 LAIR_B200_API int lair_b200_mg_unique_id(void* id128);
 LAIR_B200_API int lair_b200_mg_init(int rank, int nranks, const void* id128);
 LAIR_B200_API int lair_b200_mg_finalize(void);
+/* Measurement aid: with enable != 0 the next *getrf_mg_dev calls record 8 CUDA timing events per block step on this rank
+ * (main stream: panel landed / own next block updated / trailing update done / left interchanges done; panel +
+ * communication stream: start / factored / packed / broadcast done).  mg_timeline_read synchronises the device and
+ * returns out[b * 8 + p] = milliseconds since the start of the last call (NaN: point not taken on this rank). */
+LAIR_B200_API int lair_b200_mg_timeline(int enable);
+LAIR_B200_API int lair_b200_mg_timeline_read(float* out, int64_t cap, int64_t* nblk);
 LAIR_B200_API int lair_b200_dgetrf_mg_dev(int64_t n, int64_t nb, double* d_a_local, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
 LAIR_B200_API int lair_b200_sgetrf_mg_dev(int64_t n, int64_t nb, float* d_a_local, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
 

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "lair_b200_mg_unique_id": [vp],
     "lair_b200_mg_init": [cint, cint, vp],
     "lair_b200_mg_finalize": [],
+    "lair_b200_mg_timeline": [cint],
+    "lair_b200_mg_timeline_read": [vp, i64, ctypes.POINTER(i64)],
     "lair_b200_dgetrf_mg_dev": [i64, i64, vp, i64, vp, vp, vp],
     "lair_b200_sgetrf_mg_dev": [i64, i64, vp, i64, vp, vp, vp],
     "lair_b200_profile_begin": [],

@@ -157,6 +157,8 @@ struct Options {
     int64_t cx_blocked = 1;     // complex beyond small_n: 1 blocked sweep (blocked_cx.cu), 2 the same with single-CTA leaf panels, 0 the single-CTA in-place kernel
     int64_t qr_blocked = 1;     // f32 / f64 geqrf with min(m, n) >= 64: 1 compact-WY blocks (qr_blocked.cu), 0 one reflector at a time
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
+    int64_t mg_signal_comm = 1; // multi-GPU LU: pivots travel first on a one-CTA communicator, so the panel's wide broadcast never waits on the device (mg.cu)
+    int64_t gemm_raster = 8;    // f64 GEMM: tile columns per strip of the CTA order (1 = walk down M one tile column at a time)
 };
 
 struct Context {

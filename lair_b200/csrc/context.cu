@@ -74,6 +74,7 @@ static int init_locked(int device) {
     if (const char* v = getenv("LAIR_B200_SMALL_N")) g_ctx.opt.small_n = atoll(v);
     if (const char* v = getenv("LAIR_B200_LOOKAHEAD")) g_ctx.opt.lookahead = atoll(v);
     if (const char* v = getenv("LAIR_B200_BATCHED_CFG")) g_ctx.opt.batched_cfg = atoll(v);
+    if (const char* v = getenv("LAIR_B200_MG_SIGNAL_COMM")) g_ctx.opt.mg_signal_comm = atoll(v);
     g_ctx.ready = true;
     return LAIR_B200_OK;
 }
@@ -229,6 +230,10 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.cx_blocked = value;
     } else if (!strcmp(name, "gemm_cfg")) {
         o.gemm_cfg = value;
+    } else if (!strcmp(name, "mg_signal_comm")) {
+        o.mg_signal_comm = value;
+    } else if (!strcmp(name, "gemm_raster")) {
+        o.gemm_raster = value < 1 ? 1 : value;
     } else if (!strcmp(name, "panel_group")) {
         o.panel_group = value;
     } else if (!strcmp(name, "panel_rpt")) {
@@ -282,6 +287,8 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "qr_blocked")) *value = o.qr_blocked;
     else if (!strcmp(name, "cx_blocked")) *value = o.cx_blocked;
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
+    else if (!strcmp(name, "gemm_raster")) *value = o.gemm_raster;
+    else if (!strcmp(name, "mg_signal_comm")) *value = o.mg_signal_comm;
     else if (!strcmp(name, "panel_group")) *value = o.panel_group;
     else if (!strcmp(name, "panel_rpt")) *value = o.panel_rpt;
     else if (!strcmp(name, "panel_timing")) *value = o.panel_timing;

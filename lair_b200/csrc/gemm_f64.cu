@@ -122,15 +122,21 @@ __device__ __forceinline__ void load_stage_fast(double* __restrict__ sa, double*
 template <class C, int WARPS_M, int WARPS_N, int WTM, int WTN, int MINB, bool ALIGNED>
 __global__ void __launch_bounds__(C::THREADS, MINB)
 dgemm_minus_kernel(const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
-                   double* __restrict__ Cm, long long ldc, int M, int N, int K, int tiles_m) {
+                   double* __restrict__ Cm, long long ldc, int M, int N, int K, int tiles_m, int tiles_n, int raster) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
-    // tiles walk down M first: consecutive CTAs share the B (U12) tile column in L2
+    // CTA order: strips of `raster` tile columns, row by row inside a strip.  The CTAs resident at any time then cover
+    // (resident / raster) tile rows x raster tile columns, so an A (L21) tile is read from DRAM once per STRIP instead of
+    // once per tile column -- at M = 65 536, K = 256 the A panel is 134 MB, larger than the L2, and walking down M one
+    // tile column at a time (raster = 1) streamed it from DRAM for every one of the N / BN tile columns.
     const int tile = blockIdx.x;
-    const int m0 = (tile % tiles_m) * C::BM, n0 = (tile / tiles_m) * C::BN;
+    const int per_strip = tiles_m * raster;
+    const int strip = tile / per_strip, rem = tile - strip * per_strip;
+    const int sw = min(raster, tiles_n - strip * raster);  // the last strip may be narrower
+    const int m0 = (rem / sw) * C::BM, n0 = (strip * raster + rem % sw) * C::BN;
     const int KT = (K + BK - 1) / BK;
 
     // interior tile with aligned operands: fixed per-thread source pointers, no bounds logic
@@ -261,8 +267,10 @@ int launch(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, cons
     const int64_t tiles = tiles_m * tiles_n;
     LAIR_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
     ProfScope prof(kProfGemm, s, 2.0 * (double)m * (double)n * (double)k);
+    int64_t raster = ctx().opt.gemm_raster;
+    if (raster > tiles_n) raster = tiles_n;
     kern<<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(d_a, (long long)lda, d_b, (long long)ldb, d_c, (long long)ldc, (int)m, (int)n,
-                                                           (int)k, (int)tiles_m);
+                                                           (int)k, (int)tiles_m, (int)tiles_n, (int)raster);
     LAIR_LAUNCH_CHECK();
     return LAIR_B200_OK;
 }

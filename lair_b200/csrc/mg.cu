@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -26,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -36,6 +38,12 @@ struct NcclApi {
 struct MgState {
     NcclApi api;
     ncclComm_t comm = nullptr;
+    // A second communicator restricted to ONE CTA carries the pivots ahead of the panel.  A rank reaches the broadcast of
+    // block b+1 at the START of its update with block b, milliseconds before the owner has factored that block, and an
+    // NCCL kernel waits on the device: with the panel's own broadcast first in line, its CTAs (one per channel) sat
+    // spinning on every non-owner rank under the trailing update and cost the DMMA GEMM ~10 % (per-rank timeline,
+    // profiles/r2_mg_timeline.md).  Now the one-CTA broadcast does the waiting and the wide one starts when data flows.
+    ncclComm_t comm_sig = nullptr;
     int rank = 0, nranks = 1;
     void* wbuf[2] = {nullptr, nullptr};  // packed panels (double buffered for the lookahead)
     size_t wbytes = 0;
@@ -44,7 +52,21 @@ struct MgState {
     cudaEvent_t ev_used[2] = {nullptr, nullptr};    // compute stream finished reading wbuf[k&1]
     cudaEvent_t ev_next = nullptr;                  // next block's columns are updated (owner only)
     cudaEvent_t ev_start = nullptr;
+    // optional per-block-step timeline (lair_b200_mg_timeline): kTlPoints timing events per block step on the two streams
+    bool timeline = false;
+    std::vector<cudaEvent_t> tl;
+    int64_t tl_nblk = 0;
 };
+// timeline points of block step b (all on this rank): what the main stream M and the panel / communication stream C were doing
+enum TlPoint { kTlPanelReady = 0,   // M: the broadcast of block b has landed, the update with it may start
+               kTlNextUpdated,      // M: (owner of b+1) block b+1's own columns are updated
+               kTlPanelStart,       // C: start of factor + pack + broadcast of block b+1
+               kTlPanelDone,        // C: (owner of b+1) block b+1 factored
+               kTlPackDone,         // C: (owner of b+1) packed
+               kTlBcastDone,        // C: broadcast of block b+1 complete on this rank
+               kTlUpdateDone,       // M: trailing update with block b finished
+               kTlStepDone,         // M: left interchanges done
+               kTlPoints };
 MgState g_mg;
 
 int load_nccl(NcclApi& api) {
@@ -67,6 +89,7 @@ int load_nccl(NcclApi& api) {
     LOAD(GetUniqueId, "ncclGetUniqueId")
     LOAD(CommInitRank, "ncclCommInitRank")
     LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(CommSplit, "ncclCommSplit")
     LOAD(Broadcast, "ncclBroadcast")
     LOAD(AllReduce, "ncclAllReduce")
     LOAD(GroupStart, "ncclGroupStart")
@@ -145,6 +168,20 @@ int getrf_mg_dev(int64_t n, int64_t nb, T* d_a, int64_t lda, int32_t* d_ipiv, in
     LAIR_CUDA_CHECK(cudaStreamWaitEvent(C, mg.ev_start, 0));
 
     const int64_t nblk = D.nblocks();
+    if (mg.timeline) {
+        const size_t need_ev = (size_t)(nblk + 1) * kTlPoints;
+        while (mg.tl.size() < need_ev) {
+            cudaEvent_t e;
+            LAIR_CUDA_CHECK(cudaEventCreate(&e));
+            mg.tl.push_back(e);
+        }
+        mg.tl_nblk = nblk;
+        LAIR_CUDA_CHECK(cudaEventRecord(mg.tl[(size_t)nblk * kTlPoints], M));  // t = 0
+    }
+    auto mark = [&](int64_t blk, int point, cudaStream_t st) -> int {
+        if (mg.timeline && blk >= 0 && blk < nblk) LAIR_CUDA_CHECK(cudaEventRecord(mg.tl[(size_t)blk * kTlPoints + point], st));
+        return LAIR_B200_OK;
+    };
     // factor + pack + broadcast of block `blk` on stream C (every rank calls this in the same order)
     auto panel_and_bcast = [&](int64_t blk) -> int {
         const int64_t j0 = blk * nb, w = D.width(blk), rows = n - j0;
@@ -152,20 +189,29 @@ int getrf_mg_dev(int64_t n, int64_t nb, T* d_a, int64_t lda, int32_t* d_ipiv, in
         T* wb = static_cast<T*>(mg.wbuf[slot]);
         // wbuf[slot] was last read by the compute stream during block blk-2
         if (blk >= 2) LAIR_CUDA_CHECK(cudaStreamWaitEvent(C, mg.ev_used[slot], 0));
+        LAIR_CHECK(mark(blk - 1, kTlPanelStart, C));
         if (D.owner(blk) == D.rank) {
             const int64_t lc0 = (blk / D.P) * nb;
             LAIR_CHECK(getrf_block_dev<T>(n, d_a, lda, j0, lc0, w, d_ipiv, d_info, C));
+            LAIR_CHECK(mark(blk - 1, kTlPanelDone, C));
             const long long total = rows * w;
             int grid = (int)((total + 255) / 256);
             if (grid > 148 * 8) grid = 148 * 8;
             pack_panel_kernel<T><<<grid, 256, 0, C>>>(d_a + j0 * lda + lc0, (long long)lda, wb, rows, (int)w);
             LAIR_LAUNCH_CHECK();
+            LAIR_CHECK(mark(blk - 1, kTlPackDone, C));
         }
-        LAIR_NCCL_CHECK(mg.api.GroupStart());
-        LAIR_NCCL_CHECK(mg.api.Broadcast(wb, wb, (size_t)rows * w, dtype, D.owner(blk), mg.comm, C));
-        LAIR_NCCL_CHECK(mg.api.Broadcast(d_ipiv + j0, d_ipiv + j0, (size_t)w, ncclInt32, D.owner(blk), mg.comm, C));
-        LAIR_NCCL_CHECK(mg.api.GroupEnd());
+        if (mg.comm_sig) {
+            LAIR_NCCL_CHECK(mg.api.Broadcast(d_ipiv + j0, d_ipiv + j0, (size_t)w, ncclInt32, D.owner(blk), mg.comm_sig, C));
+            LAIR_NCCL_CHECK(mg.api.Broadcast(wb, wb, (size_t)rows * w, dtype, D.owner(blk), mg.comm, C));
+        } else {
+            LAIR_NCCL_CHECK(mg.api.GroupStart());
+            LAIR_NCCL_CHECK(mg.api.Broadcast(wb, wb, (size_t)rows * w, dtype, D.owner(blk), mg.comm, C));
+            LAIR_NCCL_CHECK(mg.api.Broadcast(d_ipiv + j0, d_ipiv + j0, (size_t)w, ncclInt32, D.owner(blk), mg.comm, C));
+            LAIR_NCCL_CHECK(mg.api.GroupEnd());
+        }
         LAIR_CUDA_CHECK(cudaEventRecord(mg.ev_bcast[slot], C));
+        LAIR_CHECK(mark(blk - 1, kTlBcastDone, C));
         return LAIR_B200_OK;
     };
     // laswp + trsm + gemm of local columns [lc_a, lc_b) with the panel of block `blk` (in wbuf)
@@ -194,6 +240,7 @@ int getrf_mg_dev(int64_t n, int64_t nb, T* d_a, int64_t lda, int32_t* d_ipiv, in
         const int slot = (int)(blk & 1);
         const int64_t j0 = blk * nb, w = D.width(blk);
         LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, mg.ev_bcast[slot], 0));
+        LAIR_CHECK(mark(blk, kTlPanelReady, M));
         const int64_t lc_right = D.first_local_col_of_block_at_or_after(blk + 1);  // local columns right of block blk
         int64_t lc_after_next = lc_right;
         if (blk + 1 < nblk) {
@@ -201,16 +248,19 @@ int getrf_mg_dev(int64_t n, int64_t nb, T* d_a, int64_t lda, int32_t* d_ipiv, in
                 // lookahead: my block blk+1 first, so its panel path + broadcast overlap the rest
                 lc_after_next = lc_right + D.width(blk + 1);
                 LAIR_CHECK(update_local(blk, lc_right, lc_after_next, M));
+                LAIR_CHECK(mark(blk, kTlNextUpdated, M));
                 LAIR_CUDA_CHECK(cudaEventRecord(mg.ev_next, M));
                 LAIR_CUDA_CHECK(cudaStreamWaitEvent(C, mg.ev_next, 0));
             }
             LAIR_CHECK(panel_and_bcast(blk + 1));
         }
         LAIR_CHECK(update_local(blk, lc_after_next, lcols, M));
+        LAIR_CHECK(mark(blk, kTlUpdateDone, M));
         // interchanges reach back into the L part stored on this rank (columns of blocks < blk,
         // and -- on the owner -- nothing of block blk itself: the panel kernel already placed its rows)
         const int64_t lc_left_end = D.first_local_col_of_block_at_or_after(blk);
         if (lc_left_end > 0) LAIR_CHECK(laswp_dev<T>(lc_left_end, d_a, lda, j0, j0 + w, d_ipiv, M));
+        LAIR_CHECK(mark(blk, kTlStepDone, M));
         LAIR_CUDA_CHECK(cudaEventRecord(mg.ev_used[slot], M));
     }
     // every rank ends with the same info: the last zero-pivot step seen by any panel owner
@@ -253,6 +303,12 @@ int lair_b200_mg_init(int rank, int nranks, const void* id128) {
     LAIR_NCCL_CHECK(mg.api.CommInitRank(&mg.comm, nranks, id, rank));
     mg.rank = rank;
     mg.nranks = nranks;
+    if (nranks > 1 && ctx().opt.mg_signal_comm) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = 1;
+        LAIR_NCCL_CHECK(mg.api.CommSplit(mg.comm, 0, rank, &mg.comm_sig, &cfg));
+    }
     int lo = 0, hi = 0;
     LAIR_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     LAIR_CUDA_CHECK(cudaStreamCreateWithPriority(&mg.comm_stream, cudaStreamNonBlocking, hi));
@@ -267,6 +323,8 @@ int lair_b200_mg_finalize(void) {
     MgState& mg = g_mg;
     if (!mg.comm) return LAIR_B200_OK;
     cudaDeviceSynchronize();
+    if (mg.comm_sig) mg.api.CommDestroy(mg.comm_sig);
+    mg.comm_sig = nullptr;
     mg.api.CommDestroy(mg.comm);
     mg.comm = nullptr;
     for (auto& w : mg.wbuf) {
@@ -280,6 +338,36 @@ int lair_b200_mg_finalize(void) {
     for (auto& e : mg.ev_used) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (mg.ev_next) { cudaEventDestroy(mg.ev_next); mg.ev_next = nullptr; }
     if (mg.ev_start) { cudaEventDestroy(mg.ev_start); mg.ev_start = nullptr; }
+    for (auto& e : mg.tl) cudaEventDestroy(e);
+    mg.tl.clear();
+    mg.tl_nblk = 0;
+    return LAIR_B200_OK;
+}
+
+int lair_b200_mg_timeline(int enable) {
+    g_mg.timeline = enable != 0;
+    return LAIR_B200_OK;
+}
+
+// out[b * 8 + p] = milliseconds from the start of the last getrf_mg_dev call to timeline point p of block step b on this
+// rank (NaN: the point was not recorded on this rank, e.g. a non-owner's panel).  Returns the points through *nblk.
+int lair_b200_mg_timeline_read(float* out, int64_t cap, int64_t* nblk_out) {
+    MgState& mg = g_mg;
+    LAIR_REQUIRE(out && nblk_out, "mg_timeline_read: null pointer");
+    *nblk_out = mg.tl_nblk;
+    LAIR_REQUIRE(cap >= mg.tl_nblk * kTlPoints, "mg_timeline_read: buffer too small");
+    LAIR_CUDA_CHECK(cudaDeviceSynchronize());
+    if (mg.tl_nblk == 0) return LAIR_B200_OK;
+    cudaEvent_t t0 = mg.tl[(size_t)mg.tl_nblk * kTlPoints];
+    for (int64_t i = 0; i < mg.tl_nblk * kTlPoints; ++i) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, t0, mg.tl[(size_t)i]);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            ms = __builtin_nanf("");
+        }
+        out[i] = ms;
+    }
     return LAIR_B200_OK;
 }
 

@@ -63,6 +63,8 @@ extern "C" {
     pub fn lair_b200_mg_unique_id(id128: *mut c_void) -> c_int;
     pub fn lair_b200_mg_init(rank: c_int, nranks: c_int, id128: *const c_void) -> c_int;
     pub fn lair_b200_mg_finalize() -> c_int;
+    pub fn lair_b200_mg_timeline(enable: c_int) -> c_int;
+    pub fn lair_b200_mg_timeline_read(out: *mut f32, cap: i64, nblk: *mut i64) -> c_int;
     pub fn lair_b200_sgetrf_mg_dev(n: i64, nb: i64, d_a_local: *mut f32, lda: i64, d_ipiv: *mut i32, d_info: *mut i32,
                                    stream: *mut c_void) -> c_int;
     pub fn lair_b200_dgetrf_mg_dev(n: i64, nb: i64, d_a_local: *mut f64, lda: i64, d_ipiv: *mut i32, d_info: *mut i32,
