@@ -204,6 +204,8 @@ int launch_batched(long long batch, int n, T* d_a, int32_t* d_ipiv, int32_t* d_i
     size_t smem = (size_t)WARPS * (N * LD + 2 * LD) * sizeof(T);
     static bool configured = false;
     static int blocks_per_sm = 1;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) configured = false;
     if (!configured) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LAIR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem));
@@ -230,8 +232,10 @@ int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t
     LAIR_REQUIRE(d_a && d_ipiv && d_info, "batched getrf: null pointer");
     const bool full = (n == 32) && (reinterpret_cast<uintptr_t>(d_a) % 16 == 0);
     // Tuning variants (option "batched_cfg", bit field): bit 0 = tighter register bound (more resident
-    // warps), bit 1 = coarse-key arg-max, bit 2 = pivot row consumed from shared memory; 8 / 16 / 32 / 64
-    // select the later kernels (batched_lu2/3/4.cu).  The default was picked on a B200.
+    // warps), bit 1 = coarse-key arg-max, bit 2 = pivot row consumed from shared memory; 32 / 128 / 256
+    // select the later kernels (batched_lu4.cu, batched_lu5.cu).  The default was picked on a B200.  (Round 2 removed the
+    // generations that lost every A/B of round 1 -- two matrices per warp x2 (cfg 8, 64), branch-free v3 (16), look-ahead
+    // pivoting v7 (130/131): numbers in profiles/r1b_batched_v4.md.)
     constexpr int kLo = sizeof(T) == 8 ? 3 : 5;
     constexpr int kHi = sizeof(T) == 8 ? 4 : 8;
     int64_t cfg = ctx().opt.batched_cfg;
@@ -241,10 +245,7 @@ int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t
     if (!full) return launch_batched<T, 4, kLo, false, 0>(batch, (int)n, d_a, d_ipiv, d_info, s);
     if (cfg & 256) return getrf_batched32v8_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 15), s);  // shuffle broadcast, no per-step shared-memory traffic
     if (cfg & 128) return getrf_batched32v6_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 7), s);  // bit 1: look-ahead pivoting (f32), bit 2: 8-byte winner stores (f32)  // straight-line column loop + exact fallback
-    if (cfg & 64) return getrf_batched32v5_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // f32: two matrices per warp, two rows per lane
     if (cfg & 32) return getrf_batched32v4_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // retiring rows, NaN-poisoned lanes
-    if (cfg & 16) return getrf_batched32v3_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // one warp per CTA, branch-free
-    if (cfg & 8) return getrf_batched32x2_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // two matrices per warp
     switch (cfg & 7) {
         case 1: return launch_batched<T, 4, kHi, true, 0>(batch, 32, d_a, d_ipiv, d_info, s);
         case 2: return launch_batched<T, 4, kLo, true, 1>(batch, 32, d_a, d_ipiv, d_info, s);

@@ -55,7 +55,7 @@ struct Factor {
             // a tall triangle (a late column chunk catching up): one persistent dataflow solve instead
             // of the launch-per-block recursion
             // (main stream only: the solver's workspace is not shared with the lookahead stream)
-            if (k > 256 && st == s && ctx().opt.trsm_dataflow >= 2) return dtrsm_ll_dev(false, k, c1 - c0, at(k0, lc0), lda, at(k0, c0), lda, st);
+            if (k > 256 && st == s && ctx().opt.trsm_dataflow >= 1) return dtrsm_ll_dev(false, k, c1 - c0, at(k0, lc0), lda, at(k0, c0), lda, st);
         }
         return trsm_lower_unit_dev<T>(k, c1 - c0, at(k0, lc0), lda, at(k0, c0), lda, st);         // trsm   (:278-283)
     }
@@ -223,15 +223,10 @@ int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const
     else
         LAIR_CHECK(laswp_dev<T>(nrhs, d_b, ldb, 0, n, d_ipiv, s));
     if constexpr (sizeof(T) == 8) {
-        if (ctx().opt.trsm_dataflow >= 2) {
+        if (ctx().opt.trsm_dataflow >= 1) {
             // flag-in-data exchange + pre-inverted diagonal blocks (trsm_ll.cu)
             LAIR_CHECK(dtrsm_ll_dev(false, n, nrhs, d_lu, lda, d_b, ldb, s));
             return dtrsm_ll_dev(true, n, nrhs, d_lu, lda, d_b, ldb, s);
-        }
-        if (ctx().opt.trsm_dataflow) {
-            // one persistent dataflow kernel per triangle (trsm_dataflow.cu)
-            LAIR_CHECK(dtrsm_dataflow_dev(false, n, nrhs, d_lu, lda, d_b, ldb, s));
-            return dtrsm_dataflow_dev(true, n, nrhs, d_lu, lda, d_b, ldb, s);
         }
     }
     LAIR_CHECK(trsm_lower_unit_dev<T>(n, nrhs, d_lu, lda, d_b, ldb, s));

@@ -10,6 +10,7 @@
 namespace lair {
 
 static std::mutex g_call_mu;  // host-pointer entry points serialise on the library stream
+std::mutex& host_call_mutex() { return g_call_mu; }
 
 // ---- dispatch ------------------------------------------------------------------------------
 template <class T> struct IsReal { static constexpr bool value = !Ops<T>::is_complex; };

@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "../../include/lair_b200.h"
@@ -151,8 +152,8 @@ struct Options {
     int64_t stream_join_div = 4; // a chunk starting at column cs joins the sweep once cs / stream_join_div columns are factored
     int64_t laswp_perm = 1;    // getrs: apply P to the right-hand sides as one collapsed permutation (laswp_perm.cu)
     int64_t fuse_swap_trsm = 1; // block steps of width <= 128: one fused laswp+trsm launch (laswp_trsm.cu)
-    int64_t trsm_dataflow = 2;  // f64 getrs: 2 flag-in-data dataflow solves with pre-inverted diagonal blocks (trsm_ll.cu),
-                                // 1 flag-word dataflow solves with substitution (trsm_dataflow.cu), 0 recursive TRSM + GEMM
+    int64_t trsm_dataflow = 2;  // f64 getrs: >= 1 flag-in-data dataflow solves with pre-inverted diagonal blocks (trsm_ll.cu),
+                                // 0 recursive TRSM + GEMM (the flag-word first generation, 4.1 ms against 2.1 ms at n = 8192 / 64 RHS, was removed in round 2)
     int64_t trsm_rb = 32;       // row-block height of the flag-word dataflow solves (32 or 64; same speed, measured)
     int64_t cx_blocked = 1;     // complex beyond small_n: 1 blocked sweep (blocked_cx.cu), 2 the same with single-CTA leaf panels, 0 the single-CTA in-place kernel
     int64_t qr_blocked = 1;     // f32 / f64 geqrf with min(m, n) >= 64: 1 compact-WY blocks (qr_blocked.cu), 0 one reflector at a time
@@ -189,6 +190,22 @@ struct Context {
 };
 
 Context& ctx();
+// Bumped every time the context is bound to a device (lair_b200_init after a shutdown): per-device caches held in
+// function-local statics (cudaFuncSetAttribute done, occupancy, largest cluster size) are redone when it changes.
+uint64_t context_epoch();
+inline bool stale_for_context(uint64_t& seen) {
+    const uint64_t e = context_epoch();
+    if (seen == e) return false;
+    seen = e;
+    return true;
+}
+// Modules that own device buffers outside Context register a hook; lair_b200_shutdown() runs them (under the call lock)
+// so a later lair_b200_init(other device) never dereferences a pointer into the old device's memory.
+void register_reset_hook(void (*fn)());
+std::mutex& host_call_mutex();  // the lock the host-pointer entry points hold (capi.cu)
+struct ResetHook {
+    explicit ResetHook(void (*fn)()) { register_reset_hook(fn); }
+};
 int ensure_init();                                  // binds to the current device if needed
 int ensure_scratch(size_t bytes, void** out);       // device scratch >= bytes (may reallocate)
 // work buffer `slot` >= bytes; a buffer that has to grow is released after `s` has drained (its users are ordered on s)
@@ -233,12 +250,6 @@ int panel_cluster_timing(long long* out8, bool clear);
 // fused laswp + unit-lower trsm for k <= 128 (laswp_trsm.cu); LAIR_B200_ERR_UNSUPPORTED beyond
 template <class T> int laswp_trsm_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k, const int32_t* d_ipiv, const T* d_l, int64_t ldl, cudaStream_t s,
                                       int64_t kp = 0);
-// 32x32 batched LU, two matrices per warp (batched_lu2.cu)
-template <class T> int getrf_batched32x2_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
-// one warp per CTA, branch-free column step, packed f32x2 updates (batched_lu3.cu)
-template <class T> int getrf_batched32v3_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
-template <> int getrf_batched32v3_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
-template <> int getrf_batched32v3_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // batched_lu4.cu: rows retire into the output tile, retired lanes are NaN-poisoned (no liveness bookkeeping)
 template <class T> int getrf_batched32v4_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v4_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
@@ -247,10 +258,6 @@ template <> int getrf_batched32v4_dev<double>(int64_t batch, double* d_a, int32_
 template <class T> int getrf_batched32v6_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v6_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v6_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
-// batched_lu4.cu, f32: two matrices per warp, two rows per lane; anything but the plain case is redone by an exact slow routine
-template <class T> int getrf_batched32v5_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
-template <> int getrf_batched32v5_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
-template <> int getrf_batched32v5_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // batched_lu5.cu: the pivot row is broadcast by shuffles, retired rows keep their values in registers
 template <class T> int getrf_batched32v8_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v8_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
@@ -261,8 +268,6 @@ template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r
 template <class T> int panel_blocked_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 template <class T> int panel_blocked_max_width(int64_t rows);
 int panel_blocked_timing(long long* out8, bool clear);
-// X = T^-1 B in place, T = unit-lower / upper triangle of d_lu (trsm_dataflow.cu)
-int dtrsm_dataflow_dev(bool upper, int64_t n, int64_t nrhs, const double* d_lu, int64_t lda, double* d_b, int64_t ldb, cudaStream_t s);
 // dst[r] = final position of the row that starts at r after the interchanges ipiv[0..k1) (laswp_perm.cu)
 int laswp_follow_dev(int64_t nrows, int64_t k1, const int32_t* d_ipiv, int32_t* d_dst, cudaStream_t s);
 // lu::Factorized::{l, u, p, into_pl} from device-resident factors (lu_extract.cu)

@@ -15,6 +15,16 @@ static thread_local char g_err[1024] = {0};
 static std::atomic<int64_t> g_launches{0};
 static Context g_ctx;
 static std::mutex g_ctx_mu;
+static std::atomic<uint64_t> g_epoch{1};
+static constexpr int kMaxHooks = 16;
+static void (*g_hooks[kMaxHooks])() = {nullptr};
+static std::atomic<int> g_nhooks{0};
+
+uint64_t context_epoch() { return g_epoch.load(std::memory_order_relaxed); }
+void register_reset_hook(void (*fn)()) {
+    const int i = g_nhooks.fetch_add(1);
+    if (i < kMaxHooks) g_hooks[i] = fn;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -75,6 +85,7 @@ static int init_locked(int device) {
     if (const char* v = getenv("LAIR_B200_LOOKAHEAD")) g_ctx.opt.lookahead = atoll(v);
     if (const char* v = getenv("LAIR_B200_BATCHED_CFG")) g_ctx.opt.batched_cfg = atoll(v);
     if (const char* v = getenv("LAIR_B200_MG_SIGNAL_COMM")) g_ctx.opt.mg_signal_comm = atoll(v);
+    g_epoch.fetch_add(1);  // per-device caches in function-local statics are stale from here on
     g_ctx.ready = true;
     return LAIR_B200_OK;
 }
@@ -174,11 +185,15 @@ int lair_b200_init(int device) {
 }
 
 int lair_b200_shutdown(void) {
+    // lock order as in the host-pointer entry points (call lock, then context lock): none of them is in flight while state goes away
+    std::lock_guard<std::mutex> call_lk(host_call_mutex());
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     Context& c = g_ctx;
     if (!c.ready) return LAIR_B200_OK;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
+    for (int i = 0; i < g_nhooks.load() && i < kMaxHooks; ++i)
+        if (g_hooks[i]) g_hooks[i]();  // module-owned device buffers (laswp_perm, trsm_ll, mg) are freed and forgotten
     if (c.panel_ws) cudaFree(c.panel_ws);
     if (c.scratch) cudaFree(c.scratch);
     for (auto& w : c.work)

@@ -195,6 +195,8 @@ int launch_gemm(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, cons
                 cudaStream_t s) {
     auto kern = GemmKernel<T>::template get<AL>();
     static bool configured = false;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) configured = false;
     if (!configured) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<T>::SMEM_BYTES));
         configured = true;

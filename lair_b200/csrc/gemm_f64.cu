@@ -259,6 +259,8 @@ int launch(int64_t m, int64_t n, int64_t k, const double* d_a, int64_t lda, cons
     using C = Cfg<WARPS_M, WARPS_N, WTM, WTN, STAGES_>;
     auto kern = dgemm_minus_kernel<C, WARPS_M, WARPS_N, WTM, WTN, MINB, AL>;
     static bool configured = false;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) configured = false;
     if (!configured) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         configured = true;

@@ -94,6 +94,8 @@ int launch_laswp(int ncols, T* d_a, int64_t lda, int k0, int k1, const int32_t* 
     int kc = (k1 - k0) < LASWP_KMAX ? (k1 - k0) : LASWP_KMAX;
     size_t smem = (size_t)2 * kc * 32 * sizeof(V);
     static size_t configured = 0;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         size_t maxb = (size_t)2 * LASWP_KMAX * 32 * sizeof(V);
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxb));

@@ -63,6 +63,11 @@ struct PermState {
     size_t bytes = 0;
 };
 PermState g_perm;
+void reset_perm_state() {
+    if (g_perm.buf) cudaFree(g_perm.buf);
+    g_perm = PermState();
+}
+ResetHook g_perm_hook(reset_perm_state);
 
 }  // namespace
 

@@ -196,6 +196,8 @@ int launch_laswp_trsm(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k,
     auto kern = laswp_trsm_kernel<T, KMAX>;
     const size_t smem = LtCfg<T, KMAX>::smem_bytes;
     static bool configured = false;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) configured = false;
     if (!configured) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;

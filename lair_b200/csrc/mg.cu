@@ -279,6 +279,9 @@ using namespace lair;
 
 extern "C" {
 
+static void reset_mg_state() { (void)lair_b200_mg_finalize(); }
+static ResetHook g_mg_hook(reset_mg_state);
+
 int lair_b200_mg_unique_id(void* id128) {
     LAIR_REQUIRE(id128 != nullptr, "mg_unique_id: null buffer");
     LAIR_CHECK(load_nccl(g_mg.api));

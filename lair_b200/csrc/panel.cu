@@ -275,6 +275,8 @@ template <class T, int W, int RPT, int MINB>
 struct PanelVariant {
     static int capacity_rows(int* grid_cap) {
         static int cached_blocks = -1;
+        static uint64_t seen_epoch = 0;
+        if (stale_for_context(seen_epoch)) cached_blocks = -1;
         if (cached_blocks < 0) {
             int b = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, panel_kernel<T, W, RPT, MINB>, PANEL_TPB, 0) != cudaSuccess) b = 0;

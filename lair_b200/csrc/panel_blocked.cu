@@ -480,6 +480,8 @@ int launch_blocked(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv
     constexpr int TPB = ROWS / RPT;
     const size_t smem = PBSmem<T, W, ROWS>::total;
     static int max_cluster = -1;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) max_cluster = -1;
     if (max_cluster < 0) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_cluster = 8;

@@ -257,6 +257,8 @@ int launch_cluster(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv
     auto kern = panel_cluster_kernel<T, W, GS>;
     const size_t smem = ClusterSmem<T, W>::total;
     static int max_cluster = -1;  // largest cluster size this device accepts for the kernel
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) max_cluster = -1;
     if (max_cluster < 0) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_cluster = 8;

@@ -169,6 +169,8 @@ int panel_cx_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, 
     const size_t limit = ctx().smem_optin > 8192 ? ctx().smem_optin - 8192 : 0;
     const int64_t cap = (int64_t)(limit / (PLD * sizeof(T)));  // rows per CTA
     static int max_cluster = -1;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) max_cluster = -1;
     if (max_cluster < 0) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         max_cluster = 8;

@@ -358,6 +358,8 @@ int qr_panel_dev(int64_t rows, int64_t w, R* d_a, int64_t lda, R* d_tau, R* d_T,
     const size_t limit = ctx().smem_optin > 20480 ? ctx().smem_optin - 20480 : 0;
     const int64_t cap = (int64_t)(limit / (QLD * sizeof(R)));
     static int max_cluster = -1;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) max_cluster = -1;
     if (max_cluster < 0) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         max_cluster = 8;

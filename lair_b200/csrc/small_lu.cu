@@ -207,6 +207,8 @@ int getrf_small_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, 
     int use_smem = need <= limit;
     size_t smem = use_smem ? need : 0;
     static size_t configured = 0;
+    static uint64_t seen_epoch = 0;
+    if (stale_for_context(seen_epoch)) configured = 0;
     if (smem > configured) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         configured = limit;
@@ -228,6 +230,8 @@ int getrs_small_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const i
     const size_t limit = ctx().smem_optin > 2048 ? ctx().smem_optin - 2048 : 0;
     LAIR_REQUIRE(smem <= limit, "getrs_small: n=%lld too large", (long long)n);
     static bool configured = false;
+    static uint64_t seen_epoch2 = 0;
+    if (stale_for_context(seen_epoch2)) configured = false;
     if (!configured) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         configured = true;

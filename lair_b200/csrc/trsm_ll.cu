@@ -309,6 +309,11 @@ struct LLState {
     int grid_cap = -1;
 };
 LLState g_ll;
+void reset_ll_state() {
+    if (g_ll.buf) cudaFree(g_ll.buf);
+    g_ll = LLState();
+}
+ResetHook g_ll_hook(reset_ll_state);
 
 }  // namespace
 
