@@ -80,7 +80,10 @@ LAIR_B200_API int lair_b200_zgetrf(int64_t m, int64_t n, void* a, int64_t row_st
  * (nrhs = 1, b_cs / x_cs ignored) and adds the multi-RHS form the reference lacks
  * (SURVEY 0.5): column r of X equals the reference's getrs on column r of B.
  * `lu` is n x n (any strides), ipiv has n entries, b / x are n x nrhs (any strides; x may
- * alias b only if their strides are identical).                                       */
+ * alias b only if their strides are identical).  ipiv must be getrf's sequential
+ * interchanges, i <= ipiv[i] < n (the reference's laswp accepts any in-range entry; the
+ * device kernels track only rows at or below the current step, so anything else is refused
+ * with LAIR_B200_ERR_INVALID instead of being mis-applied).                           */
 LAIR_B200_API int lair_b200_sgetrs(int64_t n, int64_t nrhs, const float* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const float* b, int64_t b_rs, int64_t b_cs, float* x, int64_t x_rs, int64_t x_cs);
 LAIR_B200_API int lair_b200_dgetrs(int64_t n, int64_t nrhs, const double* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const double* b, int64_t b_rs, int64_t b_cs, double* x, int64_t x_rs, int64_t x_cs);
 LAIR_B200_API int lair_b200_cgetrs(int64_t n, int64_t nrhs, const void* lu, int64_t lu_rs, int64_t lu_cs, const int64_t* ipiv, const void* b, int64_t b_rs, int64_t b_cs, void* x, int64_t x_rs, int64_t x_cs);
@@ -133,7 +136,11 @@ LAIR_B200_API int lair_b200_dgetrf_batched(int64_t batch, int64_t n, double* a, 
  * Used by the benchmark for the HBM-resident number and by callers that keep data on the
  * GPU.  Device layout is ROW-MAJOR with leading dimension `lda` (elements, >= n).
  * d_ipiv: int32[min(m,n)] global 0-based rows; d_info: int32[1].  `stream` is a
- * cudaStream_t passed as void* (NULL = default stream).  Asynchronous w.r.t. the host. */
+ * cudaStream_t passed as void* (NULL = default stream).  Asynchronous w.r.t. the host.
+ * The *_dev entry points share the context's workspaces (panel exchange slots, lookahead
+ * stream and events, scratch): use them from ONE stream at a time and not concurrently with a
+ * host-pointer entry point -- order calls on different streams with events.
+ * *laswp_dev takes the same kind of pivots as getrs (i <= d_ipiv[i]).                  */
 LAIR_B200_API int lair_b200_sgetrf_dev(int64_t m, int64_t n, float* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
 LAIR_B200_API int lair_b200_dgetrf_dev(int64_t m, int64_t n, double* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, void* stream);
 /* Complex<f32> / Complex<f64> (interleaved re, im; src/scalar.rs:370-386): beyond 128 x 128 a blocked sweep whose

@@ -60,6 +60,10 @@ static int upload_matrix_chunked(const T* a, int64_t m, int64_t n, int64_t rs, i
                                  bool* chunked) {
     *chunked = false;
     const int64_t w = ctx().opt.stream_cols;
+    // the sweep assumes the first chunk holds the first two blocks (blocked.cu: join rule cs < c0 + 2 nb + 512): a forced block
+    // width above 512 or above half a chunk would touch columns whose copy has not been waited for -- upload in one piece then
+    const int64_t nb_forced = ctx().opt.nb;
+    if (nb_forced > 512 || 2 * nb_forced > w) return LAIR_B200_OK;
     if (!IsReal<T>::value || w < 512 || fits_small<T>(m, n) || cs != 1 || rs < n || n < 2 * w || m < n / 2) return LAIR_B200_OK;
     const int nchunks = (int)((n + w - 1) / w);
     if (nchunks > Context::kMaxChunks) return LAIR_B200_OK;
@@ -115,7 +119,10 @@ template <class T>
 static int upload_ipiv32(const int64_t* ipiv, int64_t n, int32_t* d, cudaStream_t s) {
     std::vector<int32_t> p((size_t)n);
     for (int64_t i = 0; i < n; ++i) {
-        LAIR_REQUIRE(ipiv[i] >= 0 && ipiv[i] < n, "getrs: ipiv[%lld]=%lld out of range", (long long)i, (long long)ipiv[i]);
+        // LAPACK-style interchanges (what getrf returns): step i exchanges row i with a row at or below it.  The device
+        // kernels track only rows >= the current step, so an in-range entry ABOVE its step is refused, not mis-applied.
+        LAIR_REQUIRE(ipiv[i] >= i && ipiv[i] < n, "getrs: ipiv[%lld]=%lld is not in [%lld, %lld): the pivots must be getrf's sequential interchanges",
+                     (long long)i, (long long)ipiv[i], (long long)i, (long long)n);
         p[(size_t)i] = (int32_t)ipiv[i];
     }
     LAIR_CUDA_CHECK(cudaMemcpyAsync(d, p.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -318,8 +325,10 @@ static int lu_factor_host(int64_t m, int64_t n, const T* a, int64_t rs, int64_t 
 template <class T>
 static int lu_solve_host(const LuHandle* h, int64_t nrhs, const T* b, int64_t b_rs, int64_t b_cs, T* x, int64_t x_rs, int64_t x_cs) {
     LAIR_REQUIRE(nrhs >= 0, "lu_solve: negative nrhs");
-    LAIR_REQUIRE(h->m == h->n, "lu_solve: needs a square factorization (%lld x %lld); getrs.rs:18-20", (long long)h->m, (long long)h->n);
-    const int64_t n = h->n;
+    // getrs.rs:18-20 asks for a.nrows() == p.len() == b.len() and a.ncols() >= p.len(): a WIDE factorization solves with its
+    // leading m x m block
+    LAIR_REQUIRE(h->m <= h->n, "lu_solve: needs at least as many columns as rows (%lld x %lld); getrs.rs:18-20", (long long)h->m, (long long)h->n);
+    const int64_t n = h->m;
     if (n == 0 || nrhs == 0) return LAIR_B200_OK;
     LAIR_REQUIRE(b && x, "lu_solve: null pointer");
     std::lock_guard<std::mutex> lk(g_call_mu);

@@ -624,6 +624,17 @@ def test_lu_handle_errors_and_edges(lair):
         f.solve(np.zeros(4))  # not square: getrs.rs:18-20
     g = F.from_(np.eye(3))
     assert np.array_equal(g.solve(np.array([1.0, 2.0, 3.0])), np.array([1.0, 2.0, 3.0]))
+    # a WIDE factorization solves with its leading m x m block (getrs.rs:18-20: a.ncols() >= p.len())
+    rng = np.random.default_rng(5)
+    w0 = rng.uniform(0, 10, size=(3, 5))
+    bw = rng.uniform(0, 10, size=3)
+    fw = F.from_(w0.copy())
+    ref = w0.copy()
+    piv_o, _ = oracle.getrf(ref)
+    assert np.array_equal(fw.solve(bw), oracle.getrs(ref, piv_o, bw))
+    # pivots that are not sequential interchanges (entry above its step) are refused, not mis-applied
+    with pytest.raises(_ffi.LairB200Error):
+        lair.lapack.getrs(np.eye(3), [2, 0, 2], np.ones(3))
     # several factorizations coexist
     hs = [F.from_(np.eye(4) * (i + 1)) for i in range(5)]
     for i, h in enumerate(hs):
