@@ -131,6 +131,13 @@ LAIR_B200_API int lair_b200_lu_destroy(lair_b200_lu_t handle);
  * int32 (-1 = None).                                                                   */
 LAIR_B200_API int lair_b200_sgetrf_batched(int64_t batch, int64_t n, float* a, int32_t* ipiv, int32_t* info);
 LAIR_B200_API int lair_b200_dgetrf_batched(int64_t batch, int64_t n, double* a, int32_t* ipiv, int32_t* info);
+/* The same call spread over the first `ngpu` devices of the node from ONE process (independent units,
+ * contiguous slices of the batch, no collective): device d factors matrices [d*batch/ngpu, ...) with its own
+ * H2D / factor / D2H pipeline over its own PCIe link.  ngpu = 1 is the call above on device 0's streams.  Results are
+ * bit-identical to the single-GPU entry (same kernels).  Pinned host memory lets the devices overlap; pageable memory
+ * still works (the driver stages the copies).  LAIR_B200_ERR_INVALID when more GPUs are requested than are visible. */
+LAIR_B200_API int lair_b200_sgetrf_batched_mg(int64_t batch, int64_t n, float* a, int32_t* ipiv, int32_t* info, int ngpu);
+LAIR_B200_API int lair_b200_dgetrf_batched_mg(int64_t batch, int64_t n, double* a, int32_t* ipiv, int32_t* info, int ngpu);
 
 /* ---- device-resident variants (device pointers, caller's stream, no copies) -----------
  * Used by the benchmark for the HBM-resident number and by callers that keep data on the

@@ -72,6 +72,7 @@ for _p in "cz":
 for _p in "sd":
     _SIGNATURES[f"lair_b200_{_p}gesv"] = [i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp]
     _SIGNATURES[f"lair_b200_{_p}getrf_batched"] = [i64, i64, vp, vp, vp]
+    _SIGNATURES[f"lair_b200_{_p}getrf_batched_mg"] = [i64, i64, vp, vp, vp, cint]
     _SIGNATURES[f"lair_b200_{_p}getrf_dev"] = [i64, i64, vp, i64, vp, vp, vp]
     _SIGNATURES[f"lair_b200_{_p}getrs_dev"] = [i64, i64, vp, i64, vp, vp, i64, vp]
     _SIGNATURES[f"lair_b200_{_p}getrf_batched_dev"] = [i64, i64, vp, vp, vp, vp]

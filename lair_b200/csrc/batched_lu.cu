@@ -202,16 +202,19 @@ int launch_batched(long long batch, int n, T* d_a, int32_t* d_ipiv, int32_t* d_i
     constexpr int N = 32, VEC = Vec16<T>::n, LD = N + VEC;
     auto kern = batched_lu32_kernel<T, WARPS, MINB, FULL, VAR>;
     size_t smem = (size_t)WARPS * (N * LD + 2 * LD) * sizeof(T);
-    static bool configured = false;
-    static int blocks_per_sm = 1;
-    static uint64_t seen_epoch = 0;
-    if (stale_for_context(seen_epoch)) configured = false;
-    if (!configured) {
+    static KernCfg kc;
+    if (stale_for_context(kc.epoch)) kc.bps = 0, kc.devmask = 0;
+    int dev = 0;
+    LAIR_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!((kc.devmask >> dev) & 1u)) {
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAIR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-        configured = true;
+        if (kc.bps == 0) {
+            LAIR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kc.bps, kern, WARPS * 32, smem));
+            if (kc.bps < 1) kc.bps = 1;
+        }
+        kc.devmask |= 1u << dev;
     }
+    const int blocks_per_sm = kc.bps;
     long long want = (batch + WARPS - 1) / WARPS;
     long long cap = (long long)ctx().sm_count * blocks_per_sm;
     int grid = (int)(want < cap ? want : cap);

@@ -203,6 +203,14 @@ inline bool stale_for_context(uint64_t& seen) {
 // so a later lair_b200_init(other device) never dereferences a pointer into the old device's memory.
 void register_reset_hook(void (*fn)());
 std::mutex& host_call_mutex();  // the lock the host-pointer entry points hold (capi.cu)
+// Per-kernel launch configuration cached in a launcher's function-local static: resident blocks per SM (the same on
+// every B200) and the devices on which the kernel's attributes have been set (cudaFuncSetAttribute is per device; the
+// single-process multi-GPU batched entry launches the same kernel on several).
+struct KernCfg {
+    int bps = 0;
+    unsigned devmask = 0;
+    uint64_t epoch = 0;
+};
 struct ResetHook {
     explicit ResetHook(void (*fn)()) { register_reset_hook(fn); }
 };

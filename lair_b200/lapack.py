@@ -135,10 +135,11 @@ def laswp(a: np.ndarray, piv, begin: int = 0) -> None:
         view[p] = tmp
 
 
-def getrf_batched(a: np.ndarray):
+def getrf_batched(a: np.ndarray, ngpu: int = 1):
     """`batch` independent getrf calls on a C-contiguous [batch, n, n] array (n <= 32), in place.
 
-    Returns (ipiv [batch, n] int32, info [batch] int32 with -1 = None).
+    Returns (ipiv [batch, n] int32, info [batch] int32 with -1 = None).  `ngpu` > 1 spreads contiguous slices of the
+    batch over the first `ngpu` devices of the node from this one process (no collective; same bits).
     """
     if a.ndim != 3 or a.shape[1] != a.shape[2] or not a.flags.c_contiguous:
         raise ValueError("getrf_batched expects a C-contiguous [batch, n, n] array")
@@ -148,6 +149,10 @@ def getrf_batched(a: np.ndarray):
     pfx = _prefix(a)
     if pfx not in "sd":
         raise TypeError("getrf_batched supports f32 and f64")
+    if ngpu != 1:
+        fn = getattr(_ffi.lib(), f"lair_b200_{pfx}getrf_batched_mg")
+        _ffi.check(fn(batch, n, a.ctypes.data, ipiv.ctypes.data, info.ctypes.data, int(ngpu)))
+        return ipiv, info
     fn = getattr(_ffi.lib(), f"lair_b200_{pfx}getrf_batched")
     _ffi.check(fn(batch, n, a.ctypes.data, ipiv.ctypes.data, info.ctypes.data))
     return ipiv, info

@@ -58,6 +58,9 @@ extern "C" {
     // batched LU of contiguous row-major n x n matrices, n <= 32 (BASELINE configs[2]); int32 pivots / info per matrix
     pub fn lair_b200_sgetrf_batched(batch: i64, n: i64, a: *mut f32, ipiv: *mut i32, info: *mut i32) -> c_int;
     pub fn lair_b200_dgetrf_batched(batch: i64, n: i64, a: *mut f64, ipiv: *mut i32, info: *mut i32) -> c_int;
+    // the same over the first `ngpu` devices of the node, one process (contiguous slices of the batch, no collective)
+    pub fn lair_b200_sgetrf_batched_mg(batch: i64, n: i64, a: *mut f32, ipiv: *mut i32, info: *mut i32, ngpu: c_int) -> c_int;
+    pub fn lair_b200_dgetrf_batched_mg(batch: i64, n: i64, a: *mut f64, ipiv: *mut i32, info: *mut i32, ngpu: c_int) -> c_int;
 
     // one large LU over several GPUs, one process per GPU (BASELINE configs[3]); device pointers
     pub fn lair_b200_mg_unique_id(id128: *mut c_void) -> c_int;
