@@ -96,8 +96,19 @@ int queue_slice(int d, int64_t batch, int64_t n, T* a, int32_t* ipiv, int32_t* i
         LAIR_CUDA_CHECK(cudaStreamWaitEvent(b.down, b.done[i], 0));
         LAIR_CUDA_CHECK(cudaMemcpyAsync((char*)a + (size_t)b0 * mat_bytes, dAi, (size_t)nb * mat_bytes, cudaMemcpyDeviceToHost, b.down));
     }
-    // pivots and info return in one piece behind the last chunk (see getrf_batched_host, capi.cu)
-    LAIR_CUDA_CHECK(cudaMemcpyAsync(ipiv, b.dP, (size_t)batch * piv_bytes, cudaMemcpyDeviceToHost, b.down));
+    (void)ipiv;
+    (void)info;
+    return LAIR_B200_OK;
+}
+
+// Pivots and info (n + 1 int32 per matrix) return in one piece behind the last chunk -- and only after EVERY device's chunk
+// pipeline has been queued: callers usually hand in freshly allocated pageable arrays for them, and a pageable D2H blocks
+// the issuing thread until the stream has drained, which would keep the next device from even starting.
+template <class T>
+int queue_results(int d, int64_t batch, int64_t n, int32_t* ipiv, int32_t* info) {
+    LAIR_CUDA_CHECK(cudaSetDevice(d));
+    BatchDev& b = g_bd[d];
+    LAIR_CUDA_CHECK(cudaMemcpyAsync(ipiv, b.dP, (size_t)batch * n * sizeof(int32_t), cudaMemcpyDeviceToHost, b.down));
     LAIR_CUDA_CHECK(cudaMemcpyAsync(info, b.dI, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, b.down));
     return LAIR_B200_OK;
 }
@@ -124,6 +135,10 @@ int getrf_batched_mg_host(int64_t batch, int64_t n, T* a, int32_t* ipiv, int32_t
         if (cnt == 0) continue;
         status = queue_slice<T>(d, cnt, n, a + (size_t)start * n * n, ipiv + start * n, info + start, per_chunk);
         used = d + 1;
+    }
+    for (int d = 0; d < used && status == LAIR_B200_OK; ++d) {
+        const int64_t start = d * base + (d < rem ? d : rem), cnt = base + (d < rem ? 1 : 0);
+        if (cnt > 0) status = queue_results<T>(d, cnt, n, ipiv + start * n, info + start);
     }
     // wait for every device that was given work, also on failure (nothing may still write into the caller's arrays)
     for (int d = 0; d < used; ++d) {
