@@ -246,6 +246,7 @@ int getrf_batched_dev(int64_t batch, int64_t n, T* d_a, int32_t* d_ipiv, int32_t
     // cfg 129 (tighter register bound): f32 320.5 M/s (cfg 128: 310, cfg 33: 266, cfg 0: 239); f64 162.1 M/s (128: 157.4, cfg 0: 123)
     if (cfg < 0) cfg = 129;
     if (!full) return launch_batched<T, 4, kLo, false, 0>(batch, (int)n, d_a, d_ipiv, d_info, s);
+    if (cfg & 512) return getrf_batched32v9_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 3), s);  // two matrices per warp, merged winner stores
     if (cfg & 256) return getrf_batched32v8_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 15), s);  // shuffle broadcast, no per-step shared-memory traffic
     if (cfg & 128) return getrf_batched32v6_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 7), s);  // bit 1: look-ahead pivoting (f32), bit 2: 8-byte winner stores (f32)  // straight-line column loop + exact fallback
     if (cfg & 32) return getrf_batched32v4_dev<T>(batch, d_a, d_ipiv, d_info, (int)(cfg & 1), s);  // retiring rows, NaN-poisoned lanes

@@ -270,6 +270,10 @@ template <> int getrf_batched32v6_dev<double>(int64_t batch, double* d_a, int32_
 template <class T> int getrf_batched32v8_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v8_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v8_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+// batched_lu6.cu: two matrices per warp, one merged winner store for both, straight-line column step
+template <class T> int getrf_batched32v9_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v9_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+template <> int getrf_batched32v9_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 // factor one block column stored at local columns [c0, c0+w), diagonal at row r0 (blocked.cu)
 template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r0, int64_t c0, int64_t w, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
 // in-kernel blocked cluster panel (panel_blocked.cu): 8-column register sub-panels, RPT rows per thread

@@ -43,7 +43,7 @@ def test_batched32_bit_exact(lair, dt, dist):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 32, 33, 128, 129, 132, 133, 256, 260])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 32, 33, 128, 129, 132, 133, 256, 260, 512, 513])
 def test_batched32_every_variant_bit_exact(lair, dt, cfg):
     """Every tuning variant of the batched kernel (incl. two matrices per warp, one warp per CTA
     with packed f32x2 updates, retiring rows with NaN-poisoned lanes, odd batch, ties, singular, NaN, infinite and subnormal inputs) is
