@@ -159,6 +159,7 @@ struct Options {
     int64_t qr_blocked = 1;     // f32 / f64 geqrf with min(m, n) >= 64: 1 compact-WY blocks (qr_blocked.cu), 0 one reflector at a time
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
     int64_t mg_signal_comm = 1; // multi-GPU LU: pivots travel first on a one-CTA communicator, so the panel's wide broadcast never waits on the device (mg.cu)
+    int64_t sgemm_tf32 = 1;     // f32 GEMM: 1 = tcgen05 3xTF32 tensor-core path for large updates (gemm_tf32.cu), 0 = FP32 FMA kernel always
     int64_t gemm_raster = 8;    // f64 GEMM: tile columns per strip of the CTA order (1 = walk down M one tile column at a time)
 };
 
@@ -183,7 +184,7 @@ struct Context {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     // grow-only work buffers with fixed roles (ensure_work): owned by the context so shutdown releases them
-    enum WorkSlot { kWorkCxPackA0 = 0, kWorkCxPackB0, kWorkCxPackA1, kWorkCxPackB1, kWorkQr, kWorkLarf0, kWorkLarf1, kWorkSlots };
+    enum WorkSlot { kWorkCxPackA0 = 0, kWorkCxPackB0, kWorkCxPackA1, kWorkCxPackB1, kWorkQr, kWorkLarf0, kWorkLarf1, kWorkTf32Main, kWorkTf32Aux, kWorkTf32Other, kWorkSlots };
     void* work[kWorkSlots] = {};
     size_t work_bytes[kWorkSlots] = {};
     Options opt;
@@ -274,6 +275,10 @@ template <> int getrf_batched32v8_dev<double>(int64_t batch, double* d_a, int32_
 template <class T> int getrf_batched32v9_dev(int64_t batch, T* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v9_dev<float>(int64_t batch, float* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
 template <> int getrf_batched32v9_dev<double>(int64_t batch, double* d_a, int32_t* d_ipiv, int32_t* d_info, int variant, cudaStream_t s);
+// f32 C -= A B on tcgen05 tensor cores with 3xTF32-split operands (gemm_tf32.cu)
+bool sgemm_tf32x3_supported(int64_t m, int64_t n, int64_t k, const float* d_c, int64_t ldc);
+int sgemm_tf32x3_minus_dev(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
+                           int slot, cudaStream_t s);
 // factor one block column stored at local columns [c0, c0+w), diagonal at row r0 (blocked.cu)
 template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r0, int64_t c0, int64_t w, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s);
 // in-kernel blocked cluster panel (panel_blocked.cu): 8-column register sub-panels, RPT rows per thread

@@ -247,6 +247,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.gemm_cfg = value;
     } else if (!strcmp(name, "mg_signal_comm")) {
         o.mg_signal_comm = value;
+    } else if (!strcmp(name, "sgemm_tf32")) {
+        o.sgemm_tf32 = value;
     } else if (!strcmp(name, "gemm_raster")) {
         o.gemm_raster = value < 1 ? 1 : value;
     } else if (!strcmp(name, "panel_group")) {
@@ -303,6 +305,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "cx_blocked")) *value = o.cx_blocked;
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
     else if (!strcmp(name, "gemm_raster")) *value = o.gemm_raster;
+    else if (!strcmp(name, "sgemm_tf32")) *value = o.sgemm_tf32;
     else if (!strcmp(name, "mg_signal_comm")) *value = o.mg_signal_comm;
     else if (!strcmp(name, "panel_group")) *value = o.panel_group;
     else if (!strcmp(name, "panel_rpt")) *value = o.panel_rpt;

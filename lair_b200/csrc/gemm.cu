@@ -220,6 +220,13 @@ int gemm_minus_dev(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, c
     LAIR_REQUIRE(m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31), "gemm: dimension too large");
     if (m == 0 || n == 0 || k == 0) return LAIR_B200_OK;
     LAIR_REQUIRE(lda >= k && ldb >= n && ldc >= n, "gemm: leading dimension too small");
+    if constexpr (sizeof(T) == 4) {
+        // large updates go to the tensor cores (3xTF32 split, gemm_tf32.cu); one workspace per stream of the sweep
+        if (ctx().opt.sgemm_tf32 && sgemm_tf32x3_supported(m, n, k, d_c, ldc)) {
+            const int slot = s == ctx().aux_stream ? Context::kWorkTf32Aux : (s == ctx().stream ? Context::kWorkTf32Main : Context::kWorkTf32Other);
+            return sgemm_tf32x3_minus_dev(m, n, k, d_a, lda, d_b, ldb, d_c, ldc, slot, s);
+        }
+    }
     constexpr int VEC = 16 / sizeof(T);
     const bool aligned = (lda % VEC == 0) && (ldb % VEC == 0) && (reinterpret_cast<uintptr_t>(d_a) % 16 == 0) &&
                          (reinterpret_cast<uintptr_t>(d_b) % 16 == 0);
