@@ -32,7 +32,7 @@ constexpr int kStages = 3;  // 3 x 32 KB of operand tiles per CTA: two CTAs per 
 constexpr int kTileBytes = BM * BK * 4;      // 8 KB per operand tile; a stage holds A_hi, A_lo, B_hi, B_lo of one k-block
 constexpr int kStageBytes = 4 * kTileBytes;
 constexpr int kThreads = 192;
-constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kTmemCols = 256;  // columns 0-127: hi*hi; 128-255: the two small products, summed separately and added once
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,6 +72,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // kind::tf32, D = f32, A and B K-major, M = 128, N = 128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// one warp reads 32 TMEM lanes x 32 consecutive columns: lane i receives its row's 32 values
+__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
 
 struct __align__(8) Bars {
     unsigned long long full[kStages], empty[kStages], tmem_full;
@@ -135,9 +146,11 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_co
                 const uint64_t ahi = make_desc(st), alo = make_desc(st + kTileBytes), bhi = make_desc(st + 2 * kTileBytes), blo = make_desc(st + 3 * kTileBytes);
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: the descriptor's start address advances by 2 (16-byte units)
-                    umma_tf32(tmem, alo + 2 * k, bhi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
-                    umma_tf32(tmem, ahi + 2 * k, blo + 2 * k, kIdesc, 1u);
-                    umma_tf32(tmem, ahi + 2 * k, bhi + 2 * k, kIdesc, 1u);
+                    // the small products have their own accumulator: added into the running hi*hi sum one by one they
+                    // would each be rounded at the magnitude of the large sum (measured: 2.5x the error)
+                    umma_tf32(tmem + BN, alo + 2 * k, bhi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+                    umma_tf32(tmem + BN, ahi + 2 * k, blo + 2 * k, kIdesc, 1u);
+                    umma_tf32(tmem, ahi + 2 * k, bhi + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
                 }
                 umma_commit(smem_u32(&bars->empty[s]));  // the stage is free once these MMAs have read it
             }
@@ -171,16 +184,13 @@ sgemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_co
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
+            uint32_t v[32], w[32];
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                         : "r"(taddr) : "memory");
+            tmem_ld32(v, taddr);
+            tmem_ld32(w, taddr + BN);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)lane * kPitch + j * 16), "r"(v[4 * j]), "r"(v[4 * j + 1]),

@@ -768,3 +768,36 @@ def test_shutdown_then_init_rebinds_cleanly(lair):
     assert first[0] == second[0]
     for u, v in zip(first[1:], second[1:]):
         assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 32), (1000, 900, 96), (2048, 2044, 128), (4096, 3072, 256)])
+def test_sgemm_tf32x3_tensor_path_matches_f64_product(lair, shape):
+    """f32 C -= A B on the tcgen05 tensor cores (3xTF32 split, gemm_tf32.cu) against the product in f64: the error stays
+    at the level of an f32 dot product of length k (the FP32 FMA kernel's own error on the same data is the yardstick),
+    tiles that overhang m / n are handled, columns beyond n are not touched.  Contraction: src/blas/gemm.rs:6-32."""
+    import torch
+    from lair_b200 import _ffi
+    m, n, k = shape
+    pad = 4
+    L = _ffi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda")
+    g.manual_seed(m + 3 * n + 7 * k)
+    a = torch.rand(m, k, dtype=torch.float32, device="cuda", generator=g) * 2 - 1
+    b = torch.rand(k, n + pad, dtype=torch.float32, device="cuda", generator=g) * 2 - 1
+    c0 = torch.rand(m, n + pad, dtype=torch.float32, device="cuda", generator=g) * 10
+    ref = c0[:, :n].double() - a.double() @ b[:, :n].double()
+    errs = {}
+    try:
+        for mode in (1, 0):
+            _ffi.set_option("sgemm_tf32", mode)
+            c = c0.clone()
+            _ffi.check(L.lair_b200_sgemm_minus_dev(m, n, k, a.data_ptr(), k, b.data_ptr(), n + pad, c.data_ptr(), n + pad, st))
+            torch.cuda.synchronize()
+            assert torch.equal(c[:, n:], c0[:, n:]), "columns beyond n were written"
+            errs[mode] = float((c[:, :n].double() - ref).abs().max())
+    finally:
+        _ffi.set_option("sgemm_tf32", 1)
+    unit = 10 * (k ** 0.5) * 2.0 ** -24          # ~ the rounding of an f32 dot product of length k on data in [-1, 1]
+    assert errs[0] <= 4 * unit, errs
+    assert errs[1] <= 6 * unit and errs[1] <= 2 * errs[0] + unit, errs
