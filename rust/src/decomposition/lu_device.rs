@@ -1,10 +1,14 @@
 //! Optional replacement for the body of `decomposition::lu::Factorized` (src/decomposition/lu.rs:12-171)
 //! that keeps the factors in HBM between `from` and `solve`.  The public
 //! surface -- `From<ArrayBase<S, Ix2>>`, `p`, `l`, `u`, `is_singular`, `solve`, `into_pl` -- is the
-//! reference's; only the private fields change from (lu, pivots, singular) to a device handle.
+//! reference's, type parameters included: `Factorized<A, S>` with `#[derive(Debug)]`-equivalent formatting (lu.rs:11-20);
+//! only the private fields change from (lu, pivots, singular) to a device handle (`S` is kept as a marker so that
+//! code naming `lu::Factorized<f64, OwnedRepr<f64>>` keeps compiling).
 //! Source-only like the rest of this directory (no Rust toolchain in the build image); the same
 //! entry points are exercised from Python by tests/test_gpu_parity.py::test_lu_handle_*.
 use std::any::TypeId;
+use std::fmt;
+use std::marker::PhantomData;
 use std::os::raw::c_void;
 
 use ndarray::{Array1, Array2, ArrayBase, Axis, Data, DataMut, Ix1, Ix2};
@@ -17,21 +21,43 @@ const VIEW_P: i32 = 2;
 const VIEW_PL: i32 = 3;
 
 /// LU decomposition factors, device-resident.
-pub struct Factorized<A> {
+pub struct Factorized<A, S>
+where
+    A: fmt::Debug,
+    S: Data<Elem = A>,
+{
     handle: *mut c_void, // lair_b200_lu_t: owns L\U and the pivots in HBM
     rows: usize,
     cols: usize,
     singular: Option<usize>,
-    _scalar: std::marker::PhantomData<A>,
+    _marker: PhantomData<(A, S)>,
 }
 
-impl<A> Drop for Factorized<A> {
+/// The reference derives `Debug` (lu.rs:11); the factors live in HBM, so the shape, the handle and `singular` are shown.
+impl<A, S> fmt::Debug for Factorized<A, S>
+where
+    A: fmt::Debug,
+    S: Data<Elem = A>,
+{
+    fn fmt(&self, f: &mut fmt::Formatter<'_>) -> fmt::Result {
+        f.debug_struct("Factorized")
+            .field("lu", &format_args!("<{} x {} on device, handle {:p}>", self.rows, self.cols, self.handle))
+            .field("singular", &self.singular)
+            .finish()
+    }
+}
+
+impl<A, S> Drop for Factorized<A, S>
+where
+    A: fmt::Debug,
+    S: Data<Elem = A>,
+{
     fn drop(&mut self) {
         unsafe { ffi::lair_b200_lu_destroy(self.handle) };
     }
 }
 
-impl<A, S> From<ArrayBase<S, Ix2>> for Factorized<A>
+impl<A, S> From<ArrayBase<S, Ix2>> for Factorized<A, S>
 where
     A: Scalar,
     A::Real: Real,
@@ -64,14 +90,15 @@ where
             rows: a.nrows(),
             cols: a.ncols(),
             singular: if info < 0 { None } else { Some(info as usize) },
-            _scalar: std::marker::PhantomData,
+            _marker: PhantomData,
         }
     }
 }
 
-impl<A> Factorized<A>
+impl<A, S> Factorized<A, S>
 where
     A: Scalar,
+    S: Data<Elem = A>,
 {
     fn view(&self, which: i32, rows: usize, cols: usize) -> Array2<A> {
         let mut out = Array2::<A>::zeros((rows, cols));
