@@ -140,8 +140,8 @@ struct Options {
     int64_t chain_on_p = 3072;  // lookahead: while more than this many columns remain, the next block's update runs on the
                              // panel stream (no cross-stream hand-over on the chain); 0 = always on the main stream
     int64_t batched_cfg = -1; // tuning variant of the batched kernel, -1 = measured best per type (batched_lu.cu)
-    int64_t panel_cluster = 2;  // panels that fit one cluster: 2 blocked DSMEM kernel, 1 row-per-thread DSMEM kernel, 0 global-memory exchange
-    int64_t panel_rpt = 2;      // rows per thread of the blocked cluster panel kernel (1, 2, 4)
+    int64_t panel_cluster = 3;  // panels that fit one cluster: 3 record-carries-the-window kernel (panel_push.cu), 2 blocked DSMEM kernel with row pull, 1 row-per-thread DSMEM kernel, 0 global-memory exchange
+    int64_t panel_rpt = 0;      // rows per thread of the cluster panel kernels (1, 2, 4); 0 = the measured best per shape (third generation: 2)
     int64_t panel_group = 4;    // columns per compiled group body of the cluster panel kernel (2, 4, 8)
     int64_t panel_timing = 0;   // debug: accumulate per-phase cycle counts in the cluster panel kernel
     int64_t panel_w64 = 1;      // panel_blocked: take a whole 64-column block in one launch when its rows fit
@@ -285,6 +285,10 @@ template <class T> int getrf_block_dev(int64_t m, T* d_a, int64_t lda, int64_t r
 template <class T> int panel_blocked_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
 template <class T> int panel_blocked_max_width(int64_t rows);
 int panel_blocked_timing(long long* out8, bool clear);
+// fourth generation (panel_push.cu): the pushed record carries the candidate row's register window, no row pull
+template <class T> int panel_push_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t row_base, int32_t* d_info, int32_t step_base, cudaStream_t s);
+template <class T> int panel_push_max_width(int64_t rows);
+int panel_push_timing(long long* out8, bool clear);
 // dst[r] = final position of the row that starts at r after the interchanges ipiv[0..k1) (laswp_perm.cu)
 int laswp_follow_dev(int64_t nrows, int64_t k1, const int32_t* d_ipiv, int32_t* d_dst, cudaStream_t s);
 // lu::Factorized::{l, u, p, into_pl} from device-resident factors (lu_extract.cu)

@@ -331,6 +331,7 @@ int64_t lair_b200_launch_count(void) { return g_launches.load(std::memory_order_
 int lair_b200_check_fault(void* stream) { return check_fault(static_cast<cudaStream_t>(stream)); }
 
 int lair_b200_debug_panel_timing(long long* out8, int clear) {
+    if (g_ctx.opt.panel_cluster >= 3) return panel_push_timing(out8, clear != 0);
     if (g_ctx.opt.panel_cluster >= 2) return panel_blocked_timing(out8, clear != 0);
     return panel_cluster_timing(out8, clear != 0);
 }

@@ -333,6 +333,10 @@ template <> struct PanelTable<float> {
 template <class T>
 int panel_max_width(int64_t rows) {
     using PT = PanelTable<T>;
+    if (ctx().opt.panel_cluster >= 3) {
+        const int wb = panel_push_max_width<T>(rows);
+        if (wb > 0) return wb;
+    }
     if (ctx().opt.panel_cluster >= 2 && rows <= panel_cluster_max_rows()) {
         const int wb = panel_blocked_max_width<T>(rows);
         if (wb > 0) return wb;
@@ -348,6 +352,10 @@ int panel_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv, int
               int32_t step_base, cudaStream_t s) {
     using PT = PanelTable<T>;
     LAIR_REQUIRE(rows >= 1 && w >= 1 && w <= rows, "panel: bad shape rows=%lld w=%lld", (long long)rows, (long long)w);
+    if (ctx().opt.panel_cluster >= 3) {  // fourth generation: records carry the register window, every warp decides
+        int st = panel_push_dev<T>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+        if (st != LAIR_B200_ERR_UNSUPPORTED) return st;
+    }
     if (ctx().opt.panel_cluster && rows <= panel_cluster_max_rows() && (w <= 32 || ctx().opt.panel_cluster >= 2)) {
         // 2 (default): in-kernel blocked cluster kernel; 1: one-row-per-thread cluster kernel
         int st = (ctx().opt.panel_cluster >= 2) ? panel_blocked_dev<T>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s)

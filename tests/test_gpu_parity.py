@@ -287,7 +287,7 @@ def test_blocked_f64_matches_oracle(lair, shape):
     assert be <= 10 * max(be_o, 0.01), (be, be_o)
 
 
-@pytest.mark.parametrize("option,values", [("panel_cluster", (0, 1, 2)), ("panel_rpt", (1, 4, 2)), ("lookahead", (0, 1)), ("gemm_cfg", (1, 2, 3, 0)),
+@pytest.mark.parametrize("option,values", [("panel_cluster", (0, 1, 2, 3)), ("panel_rpt", (1, 4, 2, 0)), ("lookahead", (0, 1)), ("gemm_cfg", (1, 2, 3, 0)),
                                            ("nb", (64, 128, 512, 256)), ("fuse_swap_trsm", (0, 2, 1)), ("panel_exchange", (0, 1)), ("panel_w64", (0, 1)), ("chain_on_p", (0, 1))])
 def test_blocked_f64_kernel_variants(lair, option, values):
     """Every kernel variant behind a tuning option produces the oracle's pivots and L\\U."""
@@ -306,6 +306,54 @@ def test_blocked_f64_kernel_variants(lair, option, values):
             assert np.max(np.abs(a - ref)) <= 1e-9 * np.max(np.abs(ref)), (option, v)
     finally:
         _ffi.set_option(option, default)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_panel_generations_bit_identical(lair, dt):
+    """The cluster panel kernels behind `panel_cluster` (3: the pushed record carries the candidate row's register window,
+    panel_push.cu; 2: winner row pulled over DSMEM, panel_blocked.cu) keep the same operation order: pivots, singular step and
+    L\\U agree bit for bit on single-panel shapes -- ragged widths, one CTA up to 16, integer ties, a zero column, a dependent
+    column, NaN / inf and subnormal entries -- for every rows-per-thread variant, and the pivots are the oracle's."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(77)
+    rows = [200, 513, 4096, 8192] + ([12000] if dt == np.float32 else [])
+    d_cluster, d_rpt = _ffi.get_option("panel_cluster"), _ffi.get_option("panel_rpt")
+    try:
+        for m in rows:
+            for w in (7, 32, 33, 64):
+                for kind in ("rand", "ties", "zerocol", "nonfinite", "subnormal"):
+                    if kind != "rand" and m not in (513, 8192):
+                        continue
+                    a0 = _rand(rng, (m, w), dt)
+                    if kind == "ties":
+                        a0 = rng.integers(-3, 4, size=(m, w)).astype(dt)
+                    elif kind == "zerocol":
+                        a0[:, w // 2] = 0
+                        a0[:, 1] = a0[:, 0] * 2
+                    elif kind == "nonfinite":
+                        a0[m // 3, w // 3] = np.nan
+                        a0[m - 1, 0] = np.inf
+                    elif kind == "subnormal":
+                        a0[:, 2] *= dt(1e-42 if dt == np.float32 else 1e-312)
+                    _ffi.set_option("panel_cluster", 2)
+                    _ffi.set_option("panel_rpt", 2)
+                    ref = a0.copy()
+                    with np.errstate(all="ignore"):
+                        piv_r, sing_r = lair.lapack.getrf(ref)
+                    if kind == "rand" and m <= 4096:  # (the other kinds are near-tie factories: FMA vs mul + sub may pick differently)
+                        orc = a0.copy()
+                        piv_o, sing_o = oracle.getrf(orc)
+                        assert piv_r == piv_o and sing_r == sing_o, (m, w, kind)
+                    _ffi.set_option("panel_cluster", 3)
+                    for rpt in (0, 1, 2, 4):
+                        _ffi.set_option("panel_rpt", rpt)
+                        a = a0.copy()
+                        piv, sing = lair.lapack.getrf(a)
+                        assert piv == piv_r and sing == sing_r, (m, w, kind, rpt, _first_divergence(piv, piv_r))
+                        assert a.tobytes() == ref.tobytes(), (m, w, kind, rpt)
+    finally:
+        _ffi.set_option("panel_cluster", d_cluster)
+        _ffi.set_option("panel_rpt", d_rpt)
 
 
 @pytest.mark.parametrize("shape", [(1300, 1300), (1500, 1100), (1100, 1700)])

@@ -201,9 +201,9 @@ def sec_panel():
                 out(bench=f"{pfx}panel", cluster=cl, group=grp, rpt=rpt, exchange=exch, m=m, w=w, ms_best=best, ms_med=med,
                     us_per_column=best * 1e3 / w, piv_sum=int(ipiv.sum()), checksum=float(a.double().sum()))
             _ffi.set_option("panel_exchange", 1)
-            _ffi.set_option("panel_cluster", 2)
+            _ffi.set_option("panel_cluster", 3)
             _ffi.set_option("panel_group", 4)
-            _ffi.set_option("panel_rpt", 2)
+            _ffi.set_option("panel_rpt", 0)
 
 
 def sec_chain():
