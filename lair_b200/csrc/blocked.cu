@@ -20,6 +20,7 @@ struct Factor {
     int32_t* info;
     cudaStream_t s;  // the caller's stream: everything is ordered after / visible on it
     const ColumnFeed* feed = nullptr;  // columns still arriving from the host (run() only)
+    RowDrain* drain = nullptr;         // finished rows leave for the host while the sweep runs (run() only)
 
     T* at(int64_t r, int64_t c) const { return A + r * lda + c; }
 
@@ -156,6 +157,20 @@ struct Factor {
                 LAIR_CUDA_CHECK(cudaEventRecord(EP, P));
                 LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EP, 0));
             }
+            // Rows [0, j0) are final here on M's timeline: the blocks above got their left interchanges at the end of their own
+            // step, their U rows from updates M queued or P finished before EP, and later steps only touch rows >= j0.  (While
+            // column chunks are still arriving their rows are not complete yet: the drain starts when the last one has joined.)
+            if (drain && navail == n && drain->used < drain->nev && j0 - drain->drained >= drain->min_rows) {
+                cudaEvent_t& ev = drain->ev[drain->used];
+                if (!ev) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                LAIR_CUDA_CHECK(cudaEventRecord(ev, M));
+                LAIR_CUDA_CHECK(cudaStreamWaitEvent(drain->stream, ev, 0));
+                LAIR_CUDA_CHECK(cudaMemcpy2DAsync((T*)drain->host + drain->drained * drain->host_rs, (size_t)drain->host_rs * sizeof(T),
+                                                  at(drain->drained, 0), (size_t)lda * sizeof(T), (size_t)n * sizeof(T),
+                                                  (size_t)(j0 - drain->drained), cudaMemcpyDeviceToHost, drain->stream));
+                drain->drained = j0;
+                ++drain->used;
+            }
             if (nb2 > 0) {
                 if (look && chain_on_p && kmin - j0 > ctx().opt.chain_on_p) {
                     // the whole dependent chain  panel(k) -> update(next block) -> panel(k+1)  stays on P:
@@ -191,12 +206,12 @@ struct Factor {
 
 template <class T>
 int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s,
-                      const ColumnFeed* feed) {
+                      const ColumnFeed* feed, RowDrain* drain) {
     LAIR_REQUIRE(m >= 0 && n >= 0 && lda >= n, "getrf: bad shape m=%lld n=%lld lda=%lld", (long long)m, (long long)n,
                  (long long)lda);
     LAIR_REQUIRE(m < (1ll << 31) && n < (1ll << 31), "getrf: dimension too large");
     if (m == 0 || n == 0) return LAIR_B200_OK;
-    Factor<T> f{d_a, lda, m, n, d_ipiv, d_info, s, feed};
+    Factor<T> f{d_a, lda, m, n, d_ipiv, d_info, s, feed, drain};
     return f.run();
 }
 
@@ -234,7 +249,7 @@ int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const
 }
 
 #define INST(T)                                                                                          \
-    template int getrf_blocked_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, cudaStream_t, const ColumnFeed*); \
+    template int getrf_blocked_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, cudaStream_t, const ColumnFeed*, RowDrain*); \
     template int getrs_blocked_dev<T>(int64_t, int64_t, const T*, int64_t, const int32_t*, T*, int64_t, cudaStream_t);
 INST(float)
 INST(double)

@@ -23,10 +23,10 @@ static bool fits_small(int64_t m, int64_t n) {
 
 template <class T>
 int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout,
-              cudaStream_t s, const ColumnFeed* feed) {
+              cudaStream_t s, const ColumnFeed* feed, RowDrain* drain) {
     if (fits_small<T>(m, n)) return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
     if constexpr (IsReal<T>::value) {
-        return getrf_blocked_dev<T>(m, n, d_a, lda, d_ipiv, d_info, s, feed);
+        return getrf_blocked_dev<T>(m, n, d_a, lda, d_ipiv, d_info, s, feed, drain);
     } else {
         // complex beyond the single-CTA limit: blocked sweep, ZGEMM as one real GEMM on packed operands (blocked_cx.cu)
         if (ctx().opt.cx_blocked == 0) return getrf_small_dev<T>(m, n, d_a, lda, d_ipiv, d_info, std_layout, s);
@@ -104,8 +104,38 @@ static int getrf_host(int64_t m, int64_t n, T* a, int64_t rs, int64_t cs, int64_
     bool chunked = false;
     LAIR_CHECK(upload_matrix_chunked<T>(a, m, n, rs, cs, (T*)dA, ld, &feed, &chunked));
     if (!chunked) LAIR_CHECK(upload_matrix<T>(a, m, n, rs, cs, (T*)dA, ld, DevicePool::kTmpA, s));
-    LAIR_CHECK(getrf_dev<T>(m, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s, chunked ? &feed : nullptr));
-    LAIR_CHECK(download_matrix<T>(a, m, n, rs, cs, (const T*)dA, ld, DevicePool::kTmpA, s));
+    // finished rows go home while the sweep still runs: real types, row-contiguous PINNED host array (a pageable target would
+    // block this thread inside every copy), large enough for the copies to matter
+    RowDrain drain;
+    bool draining = false;
+    if (IsReal<T>::value && ctx().opt.drain_rows != 0 && !fits_small<T>(m, n) && cs == 1 && rs >= n && m >= 2048 && n >= 2048) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, a) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+            drain.host = a;
+            drain.host_rs = rs;
+            drain.stream = ctx().drain_stream;
+            drain.ev = ctx().drain_ev;
+            drain.nev = Context::kMaxChunks - 1;  // the last event is the caller's (below)
+            const int64_t by_bytes = ((int64_t)8 << 20) / (n * (int64_t)sizeof(T)) + 1, by_count = (m + Context::kMaxChunks - 2) / (Context::kMaxChunks - 1);
+            drain.min_rows = by_bytes > by_count ? by_bytes : by_count;
+            draining = true;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    LAIR_CHECK(getrf_dev<T>(m, n, (T*)dA, ld, (int32_t*)dP, (int32_t*)dI, std_layout, s, chunked ? &feed : nullptr, draining ? &drain : nullptr));
+    if (draining && drain.drained > 0) {
+        const int64_t r0 = drain.drained;  // the rows the sweep finished last
+        if (r0 < m)
+            LAIR_CUDA_CHECK(cudaMemcpy2DAsync(a + r0 * rs, (size_t)rs * sizeof(T), (const T*)dA + r0 * ld, (size_t)ld * sizeof(T), (size_t)n * sizeof(T),
+                                              (size_t)(m - r0), cudaMemcpyDeviceToHost, s));
+        cudaEvent_t& ev = ctx().drain_ev[Context::kMaxChunks - 1];  // (never handed to the sweep: nev events start at index 0 and min_rows caps their number)
+        if (!ev) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        LAIR_CUDA_CHECK(cudaEventRecord(ev, drain.stream));
+        LAIR_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));  // the wait on `s` below covers the drained rows too
+    } else {
+        LAIR_CHECK(download_matrix<T>(a, m, n, rs, cs, (const T*)dA, ld, DevicePool::kTmpA, s));
+    }
     LAIR_CHECK(download_ipiv64(ipiv, (const int32_t*)dP, k, DevicePool::kPivots64, s));
     int32_t info32 = -1;
     LAIR_CUDA_CHECK(cudaMemcpyAsync(&info32, dI, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -381,7 +411,7 @@ static int lu_view_host(const LuHandle* h, int view, T* out, int64_t rs, int64_t
 }
 
 #define INST_DISPATCH(T)                                                                                         \
-    template int getrf_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t, const ColumnFeed*); \
+    template int getrf_dev<T>(int64_t, int64_t, T*, int64_t, int32_t*, int32_t*, bool, cudaStream_t, const ColumnFeed*, RowDrain*); \
     template int getrs_dev<T>(int64_t, int64_t, const T*, int64_t, const int32_t*, T*, int64_t, cudaStream_t);
 INST_DISPATCH(float)
 INST_DISPATCH(double)

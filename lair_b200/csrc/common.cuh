@@ -158,6 +158,7 @@ struct Options {
     int64_t cx_blocked = 1;     // complex beyond small_n: 1 blocked sweep (blocked_cx.cu), 2 the same with single-CTA leaf panels, 0 the single-CTA in-place kernel
     int64_t qr_blocked = 1;     // f32 / f64 geqrf with min(m, n) >= 64: 1 compact-WY blocks (qr_blocked.cu), 0 one reflector at a time
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
+    int64_t drain_rows = 1;     // host-pointer getrf: finished rows go back to a pinned host array while the sweep runs (0 = one copy at the end)
     int64_t mg_signal_comm = 1; // multi-GPU LU: pivots travel first on a one-CTA communicator, so the panel's wide broadcast never waits on the device (mg.cu)
     int64_t sgemm_tf32 = 1;     // f32 GEMM: 1 = tcgen05 3xTF32 tensor-core path for large updates (gemm_tf32.cu), 0 = FP32 FMA kernel always
     int64_t gemm_raster = 8;    // f64 GEMM: tile columns per strip of the CTA order (1 = walk down M one tile column at a time)
@@ -176,6 +177,8 @@ struct Context {
     cudaStream_t copy_stream = nullptr;   // host -> device column chunks of the host-pointer entry points
     static constexpr int kMaxChunks = 128;
     cudaEvent_t chunk_ev[kMaxChunks] = {};  // chunk c of the matrix has landed (created on first use)
+    cudaStream_t drain_stream = nullptr;  // device -> host copies of finished rows (host-pointer getrf, RowDrain)
+    cudaEvent_t drain_ev[kMaxChunks] = {};
     // panel exchange workspace (see panel.cu)
     void* panel_ws = nullptr;
     size_t panel_ws_bytes = 0;
@@ -240,8 +243,23 @@ struct ColumnFeed {
     int nchunks = 0;
     const cudaEvent_t* ready = nullptr;
 };
+// Finished rows of the device matrix leave for the host while the sweep still runs (host-pointer getrf with a
+// row-contiguous pinned host array): once every column chunk has joined, the rows above the current block are final
+// -- later steps only interchange rows below it --, so at the start of a block step the sweep records an event on its
+// main stream and queues a strided device -> host copy of the rows finished since the last one on `stream`.
+// `drained` ends as the first row the caller still has to fetch.
+struct RowDrain {
+    void* host = nullptr;        // element (0, 0) of the host array
+    int64_t host_rs = 0;         // its row stride in elements (columns are contiguous)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t* ev = nullptr;   // nev events (created on first use)
+    int nev = 0;
+    int64_t min_rows = 0;        // rows per copy at least
+    int64_t drained = 0;
+    int used = 0;
+};
 template <class T> int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, cudaStream_t s,
-                                         const ColumnFeed* feed = nullptr);
+                                         const ColumnFeed* feed = nullptr, RowDrain* drain = nullptr);
 template <class T> int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int laswp_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s);
 template <class T> int trsm_lower_unit_dev(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* d_b, int64_t ldb, cudaStream_t s);
@@ -312,7 +330,7 @@ template <class T> int qr_q_dev(int64_t m, int64_t n, const T* d_qr, int64_t ldq
 
 // ---- dispatch helpers ----------------------------------------------------------------------
 template <class T> int getrf_dev(int64_t m, int64_t n, T* d_a, int64_t lda, int32_t* d_ipiv, int32_t* d_info, bool std_layout, cudaStream_t s,
-                                 const ColumnFeed* feed = nullptr);
+                                 const ColumnFeed* feed = nullptr, RowDrain* drain = nullptr);
 template <class T> int getrs_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 
 }  // namespace lair

@@ -78,6 +78,7 @@ static int init_locked(int device) {
     LAIR_CUDA_CHECK(cudaStreamCreateWithPriority(&g_ctx.aux_stream, cudaStreamNonBlocking, hi));
     for (auto& ev : g_ctx.ev) LAIR_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     LAIR_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    LAIR_CUDA_CHECK(cudaStreamCreateWithFlags(&g_ctx.drain_stream, cudaStreamNonBlocking));
     LAIR_CUDA_CHECK(cudaMalloc(&g_ctx.d_fault, 64));
     LAIR_CUDA_CHECK(cudaMemset(g_ctx.d_fault, 0, 64));
     if (const char* v = getenv("LAIR_B200_NB")) g_ctx.opt.nb = atoll(v);
@@ -203,6 +204,9 @@ int lair_b200_shutdown(void) {
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    if (c.drain_stream) cudaStreamDestroy(c.drain_stream);
+    for (auto& ev : c.drain_ev)
+        if (ev) cudaEventDestroy(ev);
     if (c.d_fault) cudaFree(c.d_fault);
     for (auto& ev : c.chunk_ev)
         if (ev) cudaEventDestroy(ev);
@@ -245,6 +249,8 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.cx_blocked = value;
     } else if (!strcmp(name, "gemm_cfg")) {
         o.gemm_cfg = value;
+    } else if (!strcmp(name, "drain_rows")) {
+        o.drain_rows = value;
     } else if (!strcmp(name, "mg_signal_comm")) {
         o.mg_signal_comm = value;
     } else if (!strcmp(name, "sgemm_tf32")) {
@@ -306,6 +312,7 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
     else if (!strcmp(name, "gemm_raster")) *value = o.gemm_raster;
     else if (!strcmp(name, "sgemm_tf32")) *value = o.sgemm_tf32;
+    else if (!strcmp(name, "drain_rows")) *value = o.drain_rows;
     else if (!strcmp(name, "mg_signal_comm")) *value = o.mg_signal_comm;
     else if (!strcmp(name, "panel_group")) *value = o.panel_group;
     else if (!strcmp(name, "panel_rpt")) *value = o.panel_rpt;

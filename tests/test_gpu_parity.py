@@ -384,6 +384,40 @@ def test_blocked_f64_chunked_upload(lair, shape):
         _ffi.set_option("stream_cols", default)
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(3000, 3000), (2500, 4100), (4100, 2300), (6144, 6144)])
+def test_getrf_pinned_rows_drain_while_sweeping(lair, dt, shape):
+    """Host-pointer getrf on a PINNED row-contiguous array sends finished rows home while the sweep still runs
+    (RowDrain, blocked.cu): the array and the pivots must be byte-identical to the copy-at-the-end path, with and
+    without the chunked upload, also through a padded row stride."""
+    import torch
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(shape[0] * 3 + shape[1])
+    a0 = _rand(rng, shape, dt)
+    m, n = shape
+    d_drain, d_cols = _ffi.get_option("drain_rows"), _ffi.get_option("stream_cols")
+    try:
+        for cols in (d_cols, 0):
+            _ffi.set_option("stream_cols", cols)
+            _ffi.set_option("drain_rows", 0)  # (the reference per upload mode: late column chunks catch up through other kernels)
+            ref = a0.copy()
+            piv_r, sing_r = lair.lapack.getrf(ref)
+            for pad in (0, 24):
+                _ffi.set_option("drain_rows", 1)
+                buf = torch.empty((m, n + pad), dtype=torch.float64 if dt == np.float64 else torch.float32, pin_memory=True).numpy()
+                buf[:] = -7
+                a = buf[:, :n]
+                a[:] = a0
+                piv, sing = lair.lapack.getrf(a)
+                assert piv == piv_r and sing == sing_r, (cols, pad, _first_divergence(piv, piv_r))
+                assert np.array_equal(a, ref), (cols, pad)
+                if pad:
+                    assert np.all(buf[:, n:] == -7)  # the padding columns of the host array are never written
+    finally:
+        _ffi.set_option("drain_rows", d_drain)
+        _ffi.set_option("stream_cols", d_cols)
+
+
 @pytest.mark.parametrize("shape", [(1300, 1300), (1100, 1700)])
 def test_blocked_f32_chunked_upload_backward_error(lair, shape):
     """f32 through the chunked-upload host path (late chunks catch up with laswp + recursive trsm +
