@@ -37,6 +37,13 @@ struct Factor {
         const int64_t fuse = ctx().opt.fuse_swap_trsm;
         // (a 65..128-row triangle needs 200 KB of shared memory per CTA: worth it only for the narrow
         //  update on the lookahead's critical path, measured)
+        // wide ranges (the bulk of the trailing update, off the lookahead's critical chain): interchanges as one bandwidth
+        // pass, then the whole k-row triangle in one register-tiled launch (trsm_strip.cu); 2 = also for k <= 64
+        const int64_t strip = ctx().opt.trsm_strip;
+        if (strip != 0 && c1 - c0 > 512 && k <= 256 && (k > 64 || strip == 2)) {
+            LAIR_CHECK(swap_cols(c0, c1, k0, k0 + k, st));
+            return trsm_strip_dev<T>(k, c1 - c0, at(k0, lc0), lda, at(k0, c0), lda, st);
+        }
         if ((fuse == 1 && (k <= 64 || c1 - c0 <= 512)) || (fuse == 2 && c1 - c0 <= 512)) {
             const int rc = laswp_trsm_dev<T>(c1 - c0, A + c0, lda, k0, k, ipiv, at(k0, lc0), lda, st);
             if (rc != LAIR_B200_ERR_UNSUPPORTED) return rc;
@@ -110,7 +117,7 @@ struct Factor {
         // the GEMM on stream M (wide blocks = deeper K), once it is small by the panel chain on P.
         // (f32 keeps 64-wide blocks up to 8192 remaining columns: its 64-wide panel takes 8192 rows in one launch)
         const int64_t fixed_nb = ctx().opt.nb, t2 = ctx().opt.nb_t2;
-        const int64_t t1 = ctx().opt.nb_t1 > 0 ? ctx().opt.nb_t1 : (sizeof(T) == 8 ? 6144 : 8192);
+        const int64_t t1 = ctx().opt.nb_t1 > 0 ? ctx().opt.nb_t1 : 6144;  // (re-measured with the fourth-generation panel: profiles/r2t_probe_tune.jsonl)
         auto pick = [&](int64_t j) {
             const int64_t rem = kmin - j;
             const int64_t v = fixed_nb > 0 ? fixed_nb : (rem > t2 ? 256 : (rem > t1 ? 128 : 64));

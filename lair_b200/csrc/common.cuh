@@ -158,6 +158,7 @@ struct Options {
     int64_t cx_blocked = 1;     // complex beyond small_n: 1 blocked sweep (blocked_cx.cu), 2 the same with single-CTA leaf panels, 0 the single-CTA in-place kernel
     int64_t qr_blocked = 1;     // f32 / f64 geqrf with min(m, n) >= 64: 1 compact-WY blocks (qr_blocked.cu), 0 one reflector at a time
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
+    int64_t trsm_strip = 2;     // trailing update on wide column ranges: laswp + one register-tiled triangle launch (trsm_strip.cu); 1 = only for k > 64, 0 = chain of fused 64-row launches
     int64_t drain_rows = 1;     // host-pointer getrf: finished rows go back to a pinned host array while the sweep runs (0 = one copy at the end)
     int64_t mg_signal_comm = 1; // multi-GPU LU: pivots travel first on a one-CTA communicator, so the panel's wide broadcast never waits on the device (mg.cu)
     int64_t sgemm_tf32 = 1;     // f32 GEMM: 1 = tcgen05 3xTF32 tensor-core path for large updates (gemm_tf32.cu), 0 = FP32 FMA kernel always
@@ -262,6 +263,8 @@ template <class T> int getrf_blocked_dev(int64_t m, int64_t n, T* d_a, int64_t l
                                          const ColumnFeed* feed = nullptr, RowDrain* drain = nullptr);
 template <class T> int getrs_blocked_dev(int64_t n, int64_t nrhs, const T* d_lu, int64_t lda, const int32_t* d_ipiv, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int laswp_dev(int64_t ncols, T* d_a, int64_t lda, int64_t k0, int64_t k1, const int32_t* d_ipiv, cudaStream_t s);
+// whole k <= 256 unit-lower solve of a wide row block in one launch (trsm_strip.cu); ERR_UNSUPPORTED beyond
+template <class T> int trsm_strip_dev(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int trsm_lower_unit_dev(int64_t k, int64_t ncols, const T* d_l, int64_t ldl, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int trsm_upper_dev(int64_t k, int64_t ncols, const T* d_u, int64_t ldu, T* d_b, int64_t ldb, cudaStream_t s);
 template <class T> int gemm_minus_dev(int64_t m, int64_t n, int64_t k, const T* d_a, int64_t lda, const T* d_b, int64_t ldb, T* d_c, int64_t ldc, cudaStream_t s);

@@ -4,10 +4,13 @@
 // HBM-bound.  The sequential interchanges are first collapsed into their net effect: every
 // thread follows one touched row through the <= 128 transpositions of a pass (pure index
 // work in shared memory), which yields a list of (src -> dst) row moves; the moves are then
-// executed as a gather into shared memory followed by a scatter, one warp per row, lanes
-// across columns with 128-bit accesses (rows are contiguous in the row-major layout, so
-// every access is a full coalesced line).  Algorithmic traffic: 2 * moved_rows * ncols *
-// sizeof(T) bytes (each moved row read once and written once).
+// executed as a gather into shared memory followed by a scatter.  A CTA owns a strip of 128
+// bytes per row (8 lanes of 16 bytes: one full line per row segment, four rows per warp
+// instruction), so a pass stages at most 32 KB and a wide range gives hundreds of CTAs
+// (round 2: the first version owned 512-byte strips with 128 KB of staging -- one CTA of 8 warps
+// per SM, 128 CTAs for 16 384 f32 columns -- and moved 240 GB/s; profiles/r2v_probe_strip.jsonl).
+// Algorithmic traffic: 2 * moved_rows * ncols * sizeof(T) bytes (each moved row read once and
+// written once).
 #include "common.cuh"
 
 namespace lair {
@@ -26,16 +29,19 @@ template <class T, int VEC>
 __global__ void __launch_bounds__(LASWP_THREADS)
 laswp_kernel(T* __restrict__ A, long long lda, int ncols, int k0, int k1, const int32_t* __restrict__ ipiv) {
     using V = typename VecT<T, VEC>::type;
+    constexpr int LPR = (VEC > 1) ? 8 : 32;  // lanes per row segment: 8 x 16 bytes, or 32 scalars
+    constexpr int RPW = 32 / LPR;            // rows per warp instruction
     __shared__ int s_piv[LASWP_KMAX];
     __shared__ int s_src[2 * LASWP_KMAX];
     __shared__ int s_dst[2 * LASWP_KMAX];
     __shared__ int s_cnt;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    V* buf = reinterpret_cast<V*>(smem_raw);  // [moves][32]
+    V* buf = reinterpret_cast<V*>(smem_raw);  // [moves][LPR]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = LASWP_THREADS / 32;
-    const int col = (blockIdx.x * 32 + lane) * VEC;
+    const int sub = lane / LPR, ln = lane % LPR;
+    const int col = (blockIdx.x * LPR + ln) * VEC;
     const bool col_ok = col + VEC <= ncols;
 
     for (int kb = k0; kb < k1; kb += LASWP_KMAX) {
@@ -74,13 +80,15 @@ laswp_kernel(T* __restrict__ A, long long lda, int ncols, int k0, int k1, const 
         __syncthreads();
         const int nmov = s_cnt;
         if (col_ok) {
-            for (int e = warp; e < nmov; e += NW)
-                buf[e * 32 + lane] = *reinterpret_cast<const V*>(A + (long long)s_src[e] * lda + col);
+#pragma unroll 4
+            for (int e = warp * RPW + sub; e < nmov; e += NW * RPW)
+                buf[e * LPR + ln] = *reinterpret_cast<const V*>(A + (long long)s_src[e] * lda + col);
         }
         __syncthreads();
         if (col_ok) {
-            for (int e = warp; e < nmov; e += NW)
-                *reinterpret_cast<V*>(A + (long long)s_dst[e] * lda + col) = buf[e * 32 + lane];
+#pragma unroll 4
+            for (int e = warp * RPW + sub; e < nmov; e += NW * RPW)
+                *reinterpret_cast<V*>(A + (long long)s_dst[e] * lda + col) = buf[e * LPR + ln];
         }
         __syncthreads();
     }
@@ -90,18 +98,19 @@ template <class T, int VEC>
 int launch_laswp(int ncols, T* d_a, int64_t lda, int k0, int k1, const int32_t* d_ipiv, cudaStream_t s) {
     if (ncols <= 0) return LAIR_B200_OK;
     using V = typename VecT<T, VEC>::type;
+    constexpr int LPR = (VEC > 1) ? 8 : 32;
     auto kern = laswp_kernel<T, VEC>;
     int kc = (k1 - k0) < LASWP_KMAX ? (k1 - k0) : LASWP_KMAX;
-    size_t smem = (size_t)2 * kc * 32 * sizeof(V);
+    size_t smem = (size_t)2 * kc * LPR * sizeof(V);  // <= 32 KB on the 16-byte path, 64 KB for unaligned f64
     static size_t configured = 0;
     static uint64_t seen_epoch = 0;
     if (stale_for_context(seen_epoch)) configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        size_t maxb = (size_t)2 * LASWP_KMAX * 32 * sizeof(V);
+        const size_t maxb = (size_t)2 * LASWP_KMAX * LPR * sizeof(V);
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxb));
         configured = maxb;
     }
-    unsigned grid = (unsigned)((ncols + 32 * VEC - 1) / (32 * VEC));
+    unsigned grid = (unsigned)((ncols + LPR * VEC - 1) / (LPR * VEC));
     // upper bound on moved rows: 2 per interchange, each read once and written once
     ProfScope prof(kProfLaswp, s, 4.0 * (double)(k1 - k0) * (double)ncols * sizeof(T));
     kern<<<grid, LASWP_THREADS, smem, s>>>(d_a, (long long)lda, ncols, k0, k1, d_ipiv);

@@ -219,7 +219,11 @@ int getrf_mg_dev(int64_t n, int64_t nb, T* d_a, int64_t lda, int32_t* d_ipiv, in
         if (lc_b <= lc_a) return LAIR_B200_OK;
         const int64_t j0 = blk * nb, w = D.width(blk), r1 = j0 + w;
         const T* wb = static_cast<const T*>(mg.wbuf[blk & 1]);
-        if (ctx().opt.fuse_swap_trsm == 1 && w <= 256) {
+        if (ctx().opt.trsm_strip != 0 && lc_b - lc_a > 512 && w <= 256 && (w > 64 || ctx().opt.trsm_strip == 2)) {
+            // wide local ranges: interchanges as one bandwidth pass, the triangle in one register-tiled launch (trsm_strip.cu)
+            LAIR_CHECK(laswp_dev<T>(lc_b - lc_a, d_a + lc_a, lda, j0, r1, d_ipiv, st));
+            LAIR_CHECK(trsm_strip_dev<T>(w, lc_b - lc_a, wb, w, d_a + j0 * lda + lc_a, lda, st));
+        } else if (ctx().opt.fuse_swap_trsm == 1 && w <= 256) {
             // the block step as a chain of 64-row fused laswp + prefix update + trsm launches (laswp_trsm.cu),
             // L taken from the packed panel: same arithmetic as the single-GPU sweep (blocked.cu)
             for (int64_t off = 0; off < w; off += 64) {

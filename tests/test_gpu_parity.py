@@ -288,7 +288,7 @@ def test_blocked_f64_matches_oracle(lair, shape):
 
 
 @pytest.mark.parametrize("option,values", [("panel_cluster", (0, 1, 2, 3)), ("panel_rpt", (1, 4, 2, 0)), ("lookahead", (0, 1)), ("gemm_cfg", (1, 2, 3, 0)),
-                                           ("nb", (64, 128, 512, 256)), ("fuse_swap_trsm", (0, 2, 1)), ("panel_exchange", (0, 1)), ("panel_w64", (0, 1)), ("chain_on_p", (0, 1))])
+                                           ("nb", (64, 128, 512, 256)), ("fuse_swap_trsm", (0, 2, 1)), ("panel_exchange", (0, 1)), ("panel_w64", (0, 1)), ("chain_on_p", (0, 1)), ("trsm_strip", (0, 1, 2))])
 def test_blocked_f64_kernel_variants(lair, option, values):
     """Every kernel variant behind a tuning option produces the oracle's pivots and L\\U."""
     from lair_b200 import _ffi
@@ -382,6 +382,33 @@ def test_blocked_f64_chunked_upload(lair, shape):
                 assert res < 1.0, (w, res)
     finally:
         _ffi.set_option("stream_cols", default)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_trsm_strip_bit_identical_to_fused_chain(lair, dt):
+    """The one-launch register-tiled triangle solve of the wide trailing ranges (trsm_strip.cu, after one laswp pass) applies
+    the same FMAs in the same order as the chain of fused 64-row launches (laswp_trsm.cu): pivots and L\\U byte-identical
+    for every block width, including widths that leave ragged L blocks (96, 160, 224) and a ragged last block."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(5150)
+    d_strip, d_nb = _ffi.get_option("trsm_strip"), _ffi.get_option("nb")
+    try:
+        for shape in ((1777, 1777), (1500, 2300)):
+            a0 = _rand(rng, shape, dt)
+            for nb in (0, 96, 160, 224, 256):
+                _ffi.set_option("nb", nb)
+                _ffi.set_option("trsm_strip", 0)
+                ref = a0.copy()
+                piv_r, sing_r = lair.lapack.getrf(ref)
+                for strip in (1, 2):
+                    _ffi.set_option("trsm_strip", strip)
+                    a = a0.copy()
+                    piv, sing = lair.lapack.getrf(a)
+                    assert piv == piv_r and sing == sing_r, (shape, nb, strip, _first_divergence(piv, piv_r))
+                    assert a.tobytes() == ref.tobytes(), (shape, nb, strip)
+    finally:
+        _ffi.set_option("trsm_strip", d_strip)
+        _ffi.set_option("nb", d_nb)
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
