@@ -154,14 +154,18 @@ def _barrier(world: int):
 
 # ------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the batched kernel over 10^6 matrices,
-# from the committed `ncu --set full` capture (profiles/r1c_ncu_full_metrics.txt): f32 4.263 + 4.170 GB
-# against 8.32 GB algorithmic, f64 9.053 + 8.268 GB against 16.51 GB.
-NCU_TRAFFIC_C3 = {"f32": 4262975000 + 4169763000, "f64": 9052583000 + 8267601000}
-NCU_TRAFFIC_C3_SOURCE = "from capture profiles/r1c_ncu_full_metrics.txt (ncu --set full of the batched kernel at this size; not measured by this run)"
+# from the committed `ncu --set full` capture (profiles/r2f_ncu_full_metrics.txt): f32 4.277 + 4.170 GB
+# against 8.32 GB algorithmic, f64 9.050 + 8.266 GB against 16.51 GB.
+NCU_TRAFFIC_C3 = {"f32": 4277404000 + 4169983000, "f64": 9049625000 + 8265569000}
+NCU_TRAFFIC_C3_SOURCE = "from capture profiles/r2f_ncu_full_metrics.txt (ncu --set full of the batched kernel at this size; not measured by this run)"
 BATCHED_KERNEL_NAME = "batched_lu32 (batched_lu5.cu / batched_lu4.cu, chosen by batched_cfg)"
-# same counters for the largest DMMA GEMM launch of the c2 step (7808 x 7680 x 128; profiles/r1_final_ncu_full_metrics.txt):
-# 498.7 MB read + 427.7 MB written against 959 MB of algorithmic C read + write (A and B panels stay in L2).
-NCU_TRAFFIC_C2_GEMM = 498718976 + 427666176
+# same counters for the largest DMMA GEMM launch of the c2 step (7808 x 7680 x 128; profiles/r2f_ncu_full_metrics.txt):
+# 545.9 MB read + 459.2 MB written against 959 MB of algorithmic C read + write + 16 MB of A and B panels.
+NCU_TRAFFIC_C2_GEMM = 545877760 + 459216128
+# and for the first (largest) trailing update of n = 65 536 (65280 x 65280 x 256 in place; profiles/r2f_ncu_dgemm_n65536_summary.txt):
+# 51.36 GB read + 34.06 GB written against 68.45 GB algorithmic (C read + write 68.18 GB, A and B panels 0.27 GB): the 134 MB
+# A panel does not stay in the 126 MB L2 under the C stream and is read again for each of the 127 strips of 8 tile columns.
+NCU_TRAFFIC_C4_GEMM = 51357351000 + 34058381000
 
 
 def cpu_sample_c2(n_sample: int = 4096, nrhs: int = NRHS_C2, seed: int = 1):
@@ -368,7 +372,7 @@ def measure_c2(args, rank: int, world: int, local: int, sampler=None) -> dict:
                      "traffic": NCU_TRAFFIC_C2_GEMM,
                      "traffic_unit": "bytes of the step's largest launch (M x N x K = 7808 x 7680 x 128; "
                                      "dram__bytes_read.sum + dram__bytes_write.sum), algorithmic C read + write = 959 MB",
-                     "traffic_source": "from capture profiles/r1_final_ncu_full_metrics.txt (ncu --set full of that launch; not measured by this run)",
+                     "traffic_source": "from capture profiles/r2f_ncu_full_metrics.txt (ncu --set full of that launch; not measured by this run)",
                      "kernel_ms_by_family": kernel_share},
         "e2e": e2e, "e2e_getrf_pinned": e2e_getrf_pinned, "e2e_getrf_pageable": e2e_getrf_pageable,
         "gpu_launches": int(launches), "clocks": clocks,
@@ -680,8 +684,12 @@ def run_c4_single(args, rank: int, world: int, local: int) -> dict:
         "residual_scaled_PA_minus_LU_times_x": resid, "info": info_val,
         "roofline": {"bound": "tensor", "kernel": "dgemm_minus_kernel (DMMA m8n8k4 trailing update)", "achieved": gemm_tflops,
                      "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm_tflops / FP64_PEAK_TFLOPS, "peak_source": FP64_PEAK_SOURCE,
-                     "launches": gemm["launches"], "kernel_ms_in_step": gemm["ms"], "traffic": None,
-                     "traffic_note": "per-launch DRAM bytes of this kernel: see c2.roofline (ncu capture)",
+                     "launches": gemm["launches"], "kernel_ms_in_step": gemm["ms"],
+                     "traffic": NCU_TRAFFIC_C4_GEMM if n == 65536 else None,
+                     "traffic_unit": "bytes of the step's largest launch (M x N x K = 65280 x 65280 x 256; dram__bytes_read.sum + "
+                                     "dram__bytes_write.sum), algorithmic 68.45 GB (C read + write + the A and B panels once)",
+                     "traffic_source": "from capture profiles/r2f_ncu_dgemm_n65536_summary.txt (ncu --set full of that launch: 67.7 ms, "
+                                       "32.2 TFLOP/s, DMMA pipe 86.7 %; not measured by this run)",
                      "kernel_ms_by_family": kernel_share},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }

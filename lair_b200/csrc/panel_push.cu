@@ -642,7 +642,10 @@ int panel_push_dev(int64_t rows, int64_t w, T* d_a, int64_t lda, int32_t* d_ipiv
         return launch_push<T, 2, 32, PP_ROWS32>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
     }
     if constexpr (sizeof(T) == 4) {
-        if (rows <= (int64_t)PP_MAXC * 1024) return launch_push<T, 4, 32, 1024>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+        if (rows <= (int64_t)PP_MAXC * 1024) {
+            if (rpt == 4) return launch_push<T, 4, 32, 1024>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+            return launch_push<T, 2, 32, 1024>(rows, w, d_a, lda, d_ipiv, row_base, d_info, step_base, s);
+        }
     }
     return LAIR_B200_ERR_UNSUPPORTED;
 }
