@@ -100,6 +100,30 @@ struct Factor {
         return LAIR_B200_OK;
     }
 
+    // Paired update (run(): two block steps share one K = jp + jb trailing GEMM).  Block P = [pj0, pj0 + jp) is the
+    // predecessor of block B = [j0, j0 + jb); columns [ca, cb) have P's U rows but not yet P's contribution to the rows
+    // below P, and column block P already follows B's interchanges.  Brings [ca, cb) up to date with both blocks:
+    // B's interchanges, the rows of B take  -= L(P) U(P)  and are solved against L11(B), the rows below take one GEMM with
+    // K = jp + jb over the adjacent column blocks P and B.  Every element sees the same FMAs in the same order as two
+    // separate steps (P's jp eliminations, then B's), so the result is bit-identical.
+    int pair_update(int64_t pj0, int64_t jp, int64_t j0, int64_t jb, int64_t ca, int64_t cb, cudaStream_t st) const {
+        if (cb <= ca) return LAIR_B200_OK;
+        const int64_t r1 = j0 + jb;
+        if (cb - ca <= 512) {
+            // narrow (the lookahead's next block): the fused 64-row launches take P's rows as their prefix
+            for (int64_t off = 0; off < jb; off += 64) {
+                const int64_t kk = (jb - off) < 64 ? (jb - off) : 64;
+                LAIR_CHECK(laswp_trsm_dev<T>(cb - ca, A + ca, lda, j0 + off, kk, ipiv, at(j0 + off, j0 + off), lda, st, jp + off));
+            }
+        } else {
+            LAIR_CHECK(swap_cols(ca, cb, j0, r1, st));
+            LAIR_CHECK(gemm_minus_dev<T>(jb, cb - ca, jp, at(j0, pj0), lda, at(pj0, ca), lda, at(j0, ca), lda, st));
+            LAIR_CHECK(trsm_strip_dev<T>(jb, cb - ca, at(j0, j0), lda, at(j0, ca), lda, st));
+        }
+        if (r1 < m) LAIR_CHECK(gemm_minus_dev<T>(m - r1, cb - ca, jp + jb, at(r1, pj0), lda, at(pj0, ca), lda, at(r1, ca), lda, st));
+        return LAIR_B200_OK;
+    }
+
     // Right-looking sweep with one block of lookahead: the panel path of block k+1 (stream P,
     // high priority) runs under the bulk of block k's trailing update (stream M).
     //   M: wait panel(k) | left laswp | update(next block) -> EN | update(rest)
@@ -149,7 +173,11 @@ struct Factor {
             return LAIR_B200_OK;
         };
         const bool chain_on_p = ctx().opt.chain_on_p != 0;
-        cudaEvent_t EM = ctx().ev[2];
+        cudaEvent_t EM = ctx().ev[2], EL = ctx().ev[3];
+        // two block steps share one trailing GEMM while more than `pair_min` columns remain (0 = never)
+        const int64_t pair_min = (fixed_nb == 0 && sizeof(T) == 8) ? ctx().opt.pair_k512 : 0;
+        bool pend = false;
+        int64_t pj0 = 0, pjb = 0;
         if (look) {
             LAIR_CUDA_CHECK(cudaEventRecord(EN, M));  // P starts after everything already queued on the caller's stream
             LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
@@ -178,8 +206,38 @@ struct Factor {
                 drain->drained = j0;
                 ++drain->used;
             }
+            const bool on_p = look && chain_on_p && kmin - j0 > ctx().opt.chain_on_p;
+            if (pend) {
+                // block (j0, jb) is the successor of the deferred block: columns >= c0 take both blocks at once, K = pjb + jb
+                cudaStream_t X = (nb2 > 0 && on_p) ? P : M;
+                if (X == P) LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EM, 0));
+                LAIR_CHECK(swap_cols(pj0, j0, j0, j0 + jb, X));  // L of the deferred block follows this block's interchanges first
+                if (X == P) {
+                    LAIR_CUDA_CHECK(cudaEventRecord(EL, P));
+                    LAIR_CUDA_CHECK(cudaStreamWaitEvent(M, EL, 0));
+                }
+                if (nb2 > 0) {
+                    LAIR_CHECK(pair_update(pj0, pjb, j0, jb, c0, c0 + nb2, X));
+                    if (X == M && look) {
+                        LAIR_CUDA_CHECK(cudaEventRecord(EN, M));
+                        LAIR_CUDA_CHECK(cudaStreamWaitEvent(P, EN, 0));
+                    }
+                    LAIR_CHECK(rec(c0, nb2, P));
+                }
+                LAIR_CHECK(pair_update(pj0, pjb, j0, jb, c0 + nb2, navail, M));
+                LAIR_CHECK(swap_cols(0, pj0, j0, j0 + jb, M));   // the interchanges left of the deferred block
+                pend = false;
+                LAIR_CHECK(join_due(c0, nb2));
+                if (look && chain_on_p) LAIR_CUDA_CHECK(cudaEventRecord(EM, M));
+                continue;
+            }
+            // deferral: the next block still gets this block's full update (its panel needs it); the rest only the U rows,
+            // the GEMM waits for the next block so that both share one K = 512 launch (DMMA GEMM in place at n = 65 536:
+            // 32.2 TFLOP/s at K = 256, 33.6 at K = 512; profiles/r2x_probe_nb512.jsonl)
+            const bool defer = pair_min > 0 && kmin - j0 > pair_min && jb == 256 && nb2 == 256 && navail == n && c0 + nb2 < n &&
+                               (!fed || joined == feed->nchunks);
             if (nb2 > 0) {
-                if (look && chain_on_p && kmin - j0 > ctx().opt.chain_on_p) {
+                if (on_p) {
                     // the whole dependent chain  panel(k) -> update(next block) -> panel(k+1)  stays on P:
                     // no cross-stream hand-over on the critical path.  P only waits for M's previous
                     // rest-update (which touched the next block's columns), long finished when the
@@ -195,7 +253,14 @@ struct Factor {
                 }
                 LAIR_CHECK(rec(c0, nb2, P));                  // ... so its panel path can start under the rest
             }
-            LAIR_CHECK(update(j0, jb, c0 + nb2, navail, M));
+            if (defer) {
+                LAIR_CHECK(swap_solve(j0, jb, j0, c0 + nb2, navail, M));  // this block's U rows of the rest; rows below wait
+                pend = true;
+                pj0 = j0;
+                pjb = jb;
+            } else {
+                LAIR_CHECK(update(j0, jb, c0 + nb2, navail, M));
+            }
             LAIR_CHECK(swap_cols(0, j0, j0, j0 + jb, M));     // interchanges reach back into L (off the critical path)
             LAIR_CHECK(join_due(c0, nb2));                    // late column chunks catch up with blocks [0, c0): after
                                                               // the left interchanges, so L's rows match the pivots

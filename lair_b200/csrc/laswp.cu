@@ -102,13 +102,13 @@ int launch_laswp(int ncols, T* d_a, int64_t lda, int k0, int k1, const int32_t* 
     auto kern = laswp_kernel<T, VEC>;
     int kc = (k1 - k0) < LASWP_KMAX ? (k1 - k0) : LASWP_KMAX;
     size_t smem = (size_t)2 * kc * LPR * sizeof(V);  // <= 32 KB on the 16-byte path, 64 KB for unaligned f64
-    static size_t configured = 0;
+    static bool configured = false;
     static uint64_t seen_epoch = 0;
-    if (stale_for_context(seen_epoch)) configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (stale_for_context(seen_epoch)) configured = false;
+    if (!configured) {  // (always: the kernel's static tables come on top of the staging, 48 KB is not the threshold to test)
         const size_t maxb = (size_t)2 * LASWP_KMAX * LPR * sizeof(V);
         LAIR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxb));
-        configured = maxb;
+        configured = true;
     }
     unsigned grid = (unsigned)((ncols + LPR * VEC - 1) / (LPR * VEC));
     // upper bound on moved rows: 2 per interchange, each read once and written once

@@ -411,6 +411,34 @@ def test_trsm_strip_bit_identical_to_fused_chain(lair, dt):
         _ffi.set_option("nb", d_nb)
 
 
+@pytest.mark.parametrize("shape", [(4096, 4096), (5000, 5000), (5300, 4200), (3900, 5100)])
+def test_paired_k512_update_bit_identical(lair, shape):
+    """While many columns remain, two 256-wide block steps share one K = 512 trailing GEMM (blocked.cu pair_update): the
+    second block's rows take the first block's contribution and their own solve, the rows below one GEMM over both column
+    blocks.  Same FMAs in the same order: pivots and L\\U byte-identical to the step-by-step sweep (thresholds lowered so
+    that the pairing is active at test sizes; with and without the lookahead chain on the panel stream)."""
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(shape[0] + shape[1])
+    a0 = _rand(rng, shape, np.float64)
+    saved = {k: _ffi.get_option(k) for k in ("pair_k512", "nb_t1", "nb_t2", "chain_on_p")}
+    try:
+        _ffi.set_option("nb_t2", 1024)   # 256-wide blocks while more than 1024 columns remain
+        _ffi.set_option("nb_t1", 512)
+        _ffi.set_option("pair_k512", 0)
+        ref = a0.copy()
+        piv_r, sing_r = lair.lapack.getrf(ref)
+        for cop in (saved["chain_on_p"], 0, 1 << 30):
+            _ffi.set_option("chain_on_p", cop)
+            _ffi.set_option("pair_k512", 1200)
+            a = a0.copy()
+            piv, sing = lair.lapack.getrf(a)
+            assert piv == piv_r and sing == sing_r, (cop, _first_divergence(piv, piv_r))
+            assert a.tobytes() == ref.tobytes(), cop
+    finally:
+        for k, v in saved.items():
+            _ffi.set_option(k, v)
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", [(3000, 3000), (2500, 4100), (4100, 2300), (6144, 6144)])
 def test_getrf_pinned_rows_drain_while_sweeping(lair, dt, shape):
