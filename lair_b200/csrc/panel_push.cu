@@ -141,6 +141,19 @@ __device__ __forceinline__ int pp_argmax_hdr(uint32_t hi, unsigned posrow, F ful
     return __ffs(tie) - 1;
 }
 
+// Fast path of the arg-max: one REDUX on the coarse key with the lane number packed into its low five bits names the winning
+// lane at once (no vote, no find-first on the dependent chain).  `exact` comes back true when that answer may be wrong -- another
+// lane shares the truncated key, or no lane is live -- and the caller then repeats the choice with pp_argmax_hdr; the vote
+// that decides this overlaps with whatever the caller issues speculatively for the fast answer.
+__device__ __forceinline__ int pp_argmax_fast(uint32_t hi, bool& exact) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t pk = (hi & ~31u) | (31u - lane);
+    const uint32_t mp = __reduce_max_sync(kFullMask, pk);
+    const int src = 31 - (int)(mp & 31u);
+    exact = ((mp >> 5) == 0u) | (__any_sync(kFullMask, ((pk >> 5) == (mp >> 5)) && (int)lane != src) != 0);
+    return src;
+}
+
 // One cluster factors the (M x w) panel, w <= W; CTA `rank` holds rows rank*ROWS .. +ROWS in shared memory.
 template <class T, int RPT, int W, int ROWS>
 __global__ void __launch_bounds__(ROWS / RPT, 1)
@@ -308,8 +321,7 @@ panel_push_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __res
                 br = better ? r : br;
             }
             const uint32_t bhi = (bpr != PP_NOPOSROW) ? 1u + ((sizeof(KT) == 8) ? (uint32_t)((unsigned long long)bkey >> 32) : (uint32_t)bkey) : 0u;
-            const int wsrc = pp_argmax_hdr<KT>(bhi, bpr, [&]() { return bkey; });
-            if (lane == wsrc) {
+            auto write_record = [&]() {
                 unsigned char* rec = s_wc + warp * REC;
                 *reinterpret_cast<unsigned long long*>(rec + 8) = (unsigned long long)bhi | ((unsigned long long)bpr << 32);
 #pragma unroll
@@ -324,6 +336,13 @@ panel_push_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __res
                         }
                     }
                 }
+            };
+            bool ex1;
+            const int wsrc = pp_argmax_fast(bhi, ex1);
+            if (lane == wsrc) write_record();
+            if (ex1) {  // rare: coarse tie inside the warp (or no live row): the exact choice overwrites the record
+                const int w2 = pp_argmax_hdr<KT>(bhi, bpr, [&]() { return bkey; });
+                if (w2 != wsrc && lane == w2) write_record();
             }
             PP_STAMP(0);
             __syncthreads();
@@ -335,20 +354,37 @@ panel_push_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __res
                 //     window chunks at once, the header chunk when warp 1 has delivered the reciprocals
                 unsigned long long hy = (unsigned long long)PP_NOPOSROW << 32;
                 if (lane < NW) hy = *reinterpret_cast<const unsigned long long*>(s_wc + lane * REC + 8);
-                const int cw = pp_argmax_hdr<KT>((uint32_t)hy, (unsigned)(hy >> 32),
-                                                 [&]() { return lane < NW ? K::of(*reinterpret_cast<const T*>(s_wc + lane * REC + 16)) : (KT)0; });
-                PP_FINE(0);
+                bool ex2;
+                int cw = pp_argmax_fast((uint32_t)hy, ex2);
+                if (cw >= NW) cw = 0;
                 const unsigned bar = pp_smem_u32(&s_mbar[parity]);
                 if (lane == 0) pp_expect_tx(bar, (unsigned)(C * REC));
-                PP_FINE(1);
-                const unsigned char* src = s_wc + cw * REC;
                 const unsigned dst = push_dst0 + (unsigned)(parity * PP_MAXC * REC);
                 const unsigned rbar = push_bar0 + (unsigned)(parity * 8);
+                constexpr int NQ = (NCH + 1) / 2;
+                ulonglong2 wv[NQ];  // this lane's window chunks of the (speculative) winner, loaded under the tie check
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int ch = my_ch0 + 2 * q;
+                    wv[q] = *reinterpret_cast<const ulonglong2*>(s_wc + cw * REC + (ch < NCH ? ch : 0) * 16);
+                }
+                if (ex2) {  // rare: coarse tie among the warp records
+                    cw = pp_argmax_hdr<KT>((uint32_t)hy, (unsigned)(hy >> 32),
+                                           [&]() { return lane < NW ? K::of(*reinterpret_cast<const T*>(s_wc + lane * REC + 16)) : (KT)0; });
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int ch = my_ch0 + 2 * q;
+                        wv[q] = *reinterpret_cast<const ulonglong2*>(s_wc + cw * REC + (ch < NCH ? ch : 0) * 16);
+                    }
+                }
+                PP_FINE(0);
+                PP_FINE(1);
+                const unsigned char* src = s_wc + cw * REC;
                 if (my_peer < C) {
 #pragma unroll
-                    for (int q = 0; q < (NCH + 1) / 2; ++q) {
+                    for (int q = 0; q < NQ; ++q) {
                         const int ch = my_ch0 + 2 * q;
-                        if (ch > 0 && ch < NCH) pp_push16(dst + ch * 16, *reinterpret_cast<const ulonglong2*>(src + ch * 16), rbar);
+                        if (ch > 0 && ch < NCH) pp_push16(dst + ch * 16, wv[q], rbar);
                     }
                 }
                 PP_FINE(2);
@@ -376,22 +412,32 @@ panel_push_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __res
             PP_FINE(5);
             if (timing == 3 && rank == 0 && tid == 0) tcols += 1;
             const unsigned char* cbase = s_cand + parity * PP_MAXC * REC;
-            int gw;
-            {
-                unsigned long long hy = (unsigned long long)PP_NOPOSROW << 32;
-                if (lane < C) hy = *reinterpret_cast<const unsigned long long*>(cbase + lane * REC + 8);
-                gw = pp_argmax_hdr<KT>((uint32_t)hy, (unsigned)(hy >> 32),
-                                       [&]() { return lane < C ? K::of(*reinterpret_cast<const T*>(cbase + lane * REC + 16)) : (KT)0; });
-                if (gw >= C) gw = 0;
-            }
+            unsigned long long hy4 = (unsigned long long)PP_NOPOSROW << 32;
+            if (lane < C) hy4 = *reinterpret_cast<const unsigned long long*>(cbase + lane * REC + 8);
+            bool ex4;
+            int gw = pp_argmax_fast((uint32_t)hy4, ex4);
+            if (gw >= C) gw = 0;
             const unsigned char* wrec = cbase + gw * REC;
-            const ulonglong2 wh = *reinterpret_cast<const ulonglong2*>(wrec);
+            ulonglong2 wh = *reinterpret_cast<const ulonglong2*>(wrec);  // (speculative: loaded under the tie check)
             T u[SW];  // the pivot row's window: u[k] = its entry of column j + k (garbage beyond the sub-panel, never used)
 #pragma unroll
             for (int q = 0; q < SW / VEC; ++q) {
                 const V16 v = *reinterpret_cast<const V16*>(wrec + 16 + q * 16);
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) u[q * VEC + e] = v.v[e];
+            }
+            if (ex4) {  // rare: coarse tie among the CTA records
+                gw = pp_argmax_hdr<KT>((uint32_t)hy4, (unsigned)(hy4 >> 32),
+                                       [&]() { return lane < C ? K::of(*reinterpret_cast<const T*>(cbase + lane * REC + 16)) : (KT)0; });
+                if (gw >= C) gw = 0;
+                wrec = cbase + gw * REC;
+                wh = *reinterpret_cast<const ulonglong2*>(wrec);
+#pragma unroll
+                for (int q = 0; q < SW / VEC; ++q) {
+                    const V16 v = *reinterpret_cast<const V16*>(wrec + 16 + q * 16);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) u[q * VEC + e] = v.v[e];
+                }
             }
             const unsigned gpr = (unsigned)(wh.y >> 32);
             const int gpos = (int)(gpr >> 12);
