@@ -358,7 +358,9 @@ panel_push_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __res
                 int cw = pp_argmax_fast((uint32_t)hy, ex2);
                 if (cw >= NW) cw = 0;
                 const unsigned bar = pp_smem_u32(&s_mbar[parity]);
-                if (lane == 0) pp_expect_tx(bar, (unsigned)(C * REC));
+                // only the window chunks that still hold live columns travel (slots >= left are never read by anybody)
+                const int nch = 1 + (left + VEC - 1) / VEC;
+                if (lane == 0) pp_expect_tx(bar, (unsigned)(C * nch * 16));
                 const unsigned dst = push_dst0 + (unsigned)(parity * PP_MAXC * REC);
                 const unsigned rbar = push_bar0 + (unsigned)(parity * 8);
                 constexpr int NQ = (NCH + 1) / 2;
@@ -384,7 +386,7 @@ panel_push_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __res
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
                         const int ch = my_ch0 + 2 * q;
-                        if (ch > 0 && ch < NCH) pp_push16(dst + ch * 16, wv[q], rbar);
+                        if (ch > 0 && ch < nch) pp_push16(dst + ch * 16, wv[q], rbar);
                     }
                 }
                 PP_FINE(2);
