@@ -130,12 +130,22 @@ laswp_trsm_kernel(T* __restrict__ A, long long lda, int ncols, int k0, int k, co
                 const int i = rg + j * RG;
                 v[j] = (i < k) ? top[i * LDT + c] : T(0);
             }
-            for (int t = 0; t < pw; ++t) {
-                const T ub = Ub[t * LDT + c];
+            // multipliers by 128-bit broadcast loads, PVEC prefix rows at a time (same FMAs in the same order)
+            constexpr int PVEC = 16 / (int)sizeof(T);
+            struct alignas(16) PV16 { T v[PVEC]; };
+            for (int t = 0; t < pw; t += PVEC) {
+                T ub[PVEC];
+#pragma unroll
+                for (int e = 0; e < PVEC; ++e) ub[e] = (t + e < pw) ? Ub[(t + e) * LDT + c] : T(0);
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
                     const int i = rg + j * RG;
-                    if (i < k) v[j] -= Ls[i * LDL + t] * ub;
+                    if (i < k) {
+                        const PV16 l = *reinterpret_cast<const PV16*>(Ls + i * LDL + t);
+#pragma unroll
+                        for (int e = 0; e < PVEC; ++e)
+                            if (t + e < pw) v[j] -= l.v[e] * ub[e];
+                    }
                 }
             }
 #pragma unroll
