@@ -10,11 +10,17 @@
 //     shared-memory hop and a block barrier): the 16-byte record every CTA pushes with st.async
 //     carries the candidate row's 8-slot REGISTER WINDOW with it (80 bytes f64 / 48 bytes f32 per
 //     peer), so when the records have landed every warp holds the pivot row's active columns;
-//   * every warp waits on the mbarrier and repeats the (one REDUX + one vote) decision over the C
-//     record headers, which carry the coarse key ready-made: no "warp 0 decides, block barrier,
-//     everybody reads the result" hop;
-//   * 1 / pivot (getrf.rs:76) is formed once per CTA by warp 0 for all warp candidates at once,
-//     under the latency of its own REDUX + vote, and travels in the header;
+//   * every warp waits on the mbarrier and repeats the decision over the C record headers, which
+//     carry the coarse key ready-made: no "warp 0 decides, block barrier, everybody reads the
+//     result" hop;
+//   * each of the three arg-max levels (warp, CTA, cluster) is ONE REDUX on the coarse key with the
+//     lane number packed into its low five bits; the vote that detects a coarse tie overlaps the
+//     speculative loads for the fast answer and only a tie takes the exact path (pp_argmax_hdr);
+//   * 1 / pivot (getrf.rs:76) is formed by warp 1 for all warp candidates at once while warp 0
+//     reduces and pushes the window chunks, and travels in the header chunk, which goes last;
+//   * only the window chunks that still hold live columns travel;
+//   * mbarrier waits use the CTA-scope acquire (the data lands in this CTA's own shared memory; the
+//     cluster-scope form costs an L1 invalidate per wait);
 //   * the pusher's remote addresses are computed once per launch, every lane owns fixed
 //     (peer, chunk) pairs;
 //   * the rest of a pivot row (its multipliers and the parked columns, needed only at the end of

@@ -473,6 +473,38 @@ def test_getrf_pinned_rows_drain_while_sweeping(lair, dt, shape):
         _ffi.set_option("stream_cols", d_cols)
 
 
+def test_getrf_pinned_feed_drain_and_pairing_together(lair):
+    """The host-pointer getrf with everything on at once -- column chunks arriving during the sweep, finished rows draining
+    to the pinned array, two block steps sharing one trailing GEMM (thresholds lowered to test sizes) -- returns the bytes of
+    the plain path (same upload mode, no drain, no pairing)."""
+    import torch
+    from lair_b200 import _ffi
+    rng = np.random.default_rng(808)
+    m = n = 5200
+    a0 = _rand(rng, (m, n), np.float64)
+    saved = {k: _ffi.get_option(k) for k in ("pair_k512", "nb_t1", "nb_t2", "drain_rows", "stream_cols")}
+    try:
+        _ffi.set_option("nb_t2", 1024)
+        _ffi.set_option("nb_t1", 512)
+        for cols in (saved["stream_cols"], 0):
+            _ffi.set_option("stream_cols", cols)
+            _ffi.set_option("pair_k512", 0)
+            _ffi.set_option("drain_rows", 0)
+            ref = torch.empty((m, n), dtype=torch.float64, pin_memory=True).numpy()
+            ref[:] = a0
+            piv_r, sing_r = lair.lapack.getrf(ref)
+            _ffi.set_option("pair_k512", 1200)
+            _ffi.set_option("drain_rows", 1)
+            a = torch.empty((m, n), dtype=torch.float64, pin_memory=True).numpy()
+            a[:] = a0
+            piv, sing = lair.lapack.getrf(a)
+            assert piv == piv_r and sing == sing_r, (cols, _first_divergence(piv, piv_r))
+            assert a.tobytes() == ref.tobytes(), cols
+    finally:
+        for k, v in saved.items():
+            _ffi.set_option(k, v)
+
+
 @pytest.mark.parametrize("shape", [(1300, 1300), (1100, 1700)])
 def test_blocked_f32_chunked_upload_backward_error(lair, shape):
     """f32 through the chunked-upload host path (late chunks catch up with laswp + recursive trsm +
