@@ -176,6 +176,8 @@ struct Factor {
         cudaEvent_t EM = ctx().ev[2], EL = ctx().ev[3];
         // two block steps share one trailing GEMM while more than `pair_min` columns remain (0 = never)
         const int64_t pair_min = (fixed_nb == 0 && sizeof(T) == 8) ? ctx().opt.pair_k512 : 0;
+        // the same for the 128- and 64-wide blocks of the later sweep (K = 256 / 128 instead of 128 / 64), while more than `pair_small` columns remain
+        const int64_t pair_small = (fixed_nb == 0) ? (sizeof(T) == 8 ? ctx().opt.pair_small : ctx().opt.pair_small_f32) : 0;
         bool pend = false;
         int64_t pj0 = 0, pjb = 0;
         if (look) {
@@ -234,8 +236,9 @@ struct Factor {
             // deferral: the next block still gets this block's full update (its panel needs it); the rest only the U rows,
             // the GEMM waits for the next block so that both share one K = 512 launch (DMMA GEMM in place at n = 65 536:
             // 32.2 TFLOP/s at K = 256, 33.6 at K = 512; profiles/r2x_probe_nb512.jsonl)
-            const bool defer = pair_min > 0 && kmin - j0 > pair_min && jb == 256 && nb2 == 256 && navail == n && c0 + nb2 < n &&
-                               (!fed || joined == feed->nchunks);
+            const bool pair_here = (jb == 256 && pair_min > 0 && kmin - j0 > pair_min) ||
+                                   (jb < 256 && jb >= 64 && pair_small > 0 && kmin - j0 > pair_small);
+            const bool defer = pair_here && nb2 == jb && navail == n && c0 + nb2 < n && (!fed || joined == feed->nchunks);
             if (nb2 > 0) {
                 if (on_p) {
                     // the whole dependent chain  panel(k) -> update(next block) -> panel(k+1)  stays on P:

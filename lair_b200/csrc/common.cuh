@@ -159,6 +159,8 @@ struct Options {
     int64_t qr_blocked = 1;     // f32 / f64 geqrf with min(m, n) >= 64: 1 compact-WY blocks (qr_blocked.cu), 0 one reflector at a time
     int64_t gemm_cfg = 0;       // f64 GEMM tile: 0 auto, 1 big 128x64, 2 skinny 64x32, 3 128x128 (gemm_f64.cu)
     int64_t pair_k512 = 16384;  // f64 sweep: while more than this many columns remain, two 256-wide block steps share one K = 512 trailing GEMM (0 = never)
+    int64_t pair_small = 0;     // f64 sweep: 128- / 64-wide block steps share one trailing GEMM while more than this many columns remain (0 = never; measured slower at n = 4096 ... 16384 for every threshold: the deferral costs more overlap than the deeper K buys, profiles/r2z_probe_pair_small.jsonl)
+    int64_t pair_small_f32 = 0; // the same for f32
     int64_t trsm_strip = 2;     // trailing update on wide column ranges: laswp + one register-tiled triangle launch (trsm_strip.cu); 1 = only for k > 64, 0 = chain of fused 64-row launches
     int64_t drain_rows = 1;     // host-pointer getrf: finished rows go back to a pinned host array while the sweep runs (0 = one copy at the end)
     int64_t mg_signal_comm = 1; // multi-GPU LU: pivots travel first on a one-CTA communicator, so the panel's wide broadcast never waits on the device (mg.cu)

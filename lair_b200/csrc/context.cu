@@ -249,6 +249,10 @@ int lair_b200_set_option(const char* name, int64_t value) {
         o.cx_blocked = value;
     } else if (!strcmp(name, "gemm_cfg")) {
         o.gemm_cfg = value;
+    } else if (!strcmp(name, "pair_small")) {
+        o.pair_small = value;
+    } else if (!strcmp(name, "pair_small_f32")) {
+        o.pair_small_f32 = value;
     } else if (!strcmp(name, "pair_k512")) {
         o.pair_k512 = value;
     } else if (!strcmp(name, "trsm_strip")) {
@@ -316,6 +320,8 @@ int lair_b200_get_option(const char* name, int64_t* value) {
     else if (!strcmp(name, "gemm_cfg")) *value = o.gemm_cfg;
     else if (!strcmp(name, "gemm_raster")) *value = o.gemm_raster;
     else if (!strcmp(name, "sgemm_tf32")) *value = o.sgemm_tf32;
+    else if (!strcmp(name, "pair_small")) *value = o.pair_small;
+    else if (!strcmp(name, "pair_small_f32")) *value = o.pair_small_f32;
     else if (!strcmp(name, "pair_k512")) *value = o.pair_k512;
     else if (!strcmp(name, "trsm_strip")) *value = o.trsm_strip;
     else if (!strcmp(name, "drain_rows")) *value = o.drain_rows;
