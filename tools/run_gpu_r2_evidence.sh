@@ -24,3 +24,9 @@ python tools/ncu_summary.py gpurun_out/${TAG}_prof_dgemm.ncu-rep gpurun_out/${TA
 cat gpurun_out/${TAG}_ncu_full_metrics.txt
 tail -3 gpurun_out/${TAG}_bench_n1.err
 head -c 1500 gpurun_out/${TAG}_bench_n1.json
+# final verification of the tree the evidence was taken from: the whole GPU suite and the smoke entry
+timeout 1500 python -m pytest tests -m gpu -x -q --timeout=900 > gpurun_out/${TAG}_pytest_gpu.txt 2>&1
+echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.txt
+tail -3 gpurun_out/${TAG}_pytest_gpu.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${TAG}_smoke.txt 2>&1
+tail -2 gpurun_out/${TAG}_smoke.txt
