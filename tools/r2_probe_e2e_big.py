@@ -9,10 +9,12 @@ host = torch.empty(n, n, dtype=torch.float64).pin_memory()
 src = torch.rand(n, n, dtype=torch.float64, device="cuda")
 h = host.numpy()
 res = {}
-for pair in (0, 16384, 0, 16384):
+div_list = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["4"])]
+for pair, div in [(p_, d_) for d_ in div_list for p_ in ((0, 16384, 16384) if len(div_list) == 1 else (16384, 16384))]:
     _ffi.set_option("pair_k512", pair)
+    _ffi.set_option("stream_join_div", div)
     host.copy_(src); torch.cuda.synchronize()
     t0 = time.perf_counter(); piv, sing = lair_b200.lapack.getrf(h); t1 = time.perf_counter()
     chk = float(h[::4097, ::4099].sum()) + float(h[-1, -1])
-    print(json.dumps({"bench": "dgetrf_host_pinned", "n": n, "pair_k512": pair, "ms": round((t1 - t0) * 1e3, 1), "tflops": round(2 / 3 * n ** 3 / (t1 - t0) * 1e-12, 2),
+    print(json.dumps({"bench": "dgetrf_host_pinned", "n": n, "pair_k512": pair, "stream_join_div": div, "ms": round((t1 - t0) * 1e3, 1), "tflops": round(2 / 3 * n ** 3 / (t1 - t0) * 1e-12, 2),
                       "piv_sum": int(np.sum(piv)), "sample_checksum": chk, "sing": sing}), flush=True)
