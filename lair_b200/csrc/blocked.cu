@@ -140,7 +140,9 @@ struct Factor {
         // The width follows the REMAINING size: while the trailing matrix is large the sweep is bound by
         // the GEMM on stream M (wide blocks = deeper K), once it is small by the panel chain on P.
         // (f32 keeps 64-wide blocks up to 8192 remaining columns: its 64-wide panel takes 8192 rows in one launch)
-        const int64_t fixed_nb = ctx().opt.nb, t2 = ctx().opt.nb_t2;
+        const int64_t fixed_nb = ctx().opt.nb;
+        // (f32 switches to 256-wide blocks later: its tensor-core update is cheap, its panel chain is not; profiles/r2z_probe_tune2.jsonl)
+        const int64_t t2 = (sizeof(T) == 4 && ctx().opt.nb_t2 == 10240) ? 12288 : ctx().opt.nb_t2;
         const int64_t t1 = ctx().opt.nb_t1 > 0 ? ctx().opt.nb_t1 : 6144;  // (re-measured with the fourth-generation panel: profiles/r2t_probe_tune.jsonl)
         auto pick = [&](int64_t j) {
             const int64_t rem = kmin - j;
