@@ -139,7 +139,7 @@ struct Factor {
         // the DMMA kernel with a deeper K); measured on B200, profiles/r1_bench_history.md
         // The width follows the REMAINING size: while the trailing matrix is large the sweep is bound by
         // the GEMM on stream M (wide blocks = deeper K), once it is small by the panel chain on P.
-        // (f32 keeps 64-wide blocks up to 8192 remaining columns: its 64-wide panel takes 8192 rows in one launch)
+        // (round 1 kept f32 at 64-wide blocks up to 8192 remaining columns; with the round-2 panel kernel both types switch at 6144)
         const int64_t fixed_nb = ctx().opt.nb;
         // (f32 switches to 256-wide blocks later: its tensor-core update is cheap, its panel chain is not; profiles/r2z_probe_tune2.jsonl)
         const int64_t t2 = (sizeof(T) == 4 && ctx().opt.nb_t2 == 10240) ? 12288 : ctx().opt.nb_t2;

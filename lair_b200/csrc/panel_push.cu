@@ -356,7 +356,7 @@ panel_push_kernel(T* __restrict__ A, long long lda, int M, int w, int32_t* __res
             if (timing == 3 && rank == 0 && tid == 0) tprev = clock64();
 
             if (warp == 0) {
-                // (2) warp 0: CTA candidate among the NW warp records (one REDUX + one vote), then the record to every CTA:
+                // (2) warp 0: CTA candidate among the NW warp records (fast arg-max, exact only on a coarse tie), then the record to every CTA:
                 //     window chunks at once, the header chunk when warp 1 has delivered the reciprocals
                 unsigned long long hy = (unsigned long long)PP_NOPOSROW << 32;
                 if (lane < NW) hy = *reinterpret_cast<const unsigned long long*>(s_wc + lane * REC + 8);
